@@ -1,0 +1,101 @@
+/*
+ * cvd.h — C-ABI of libcvd_sm100.so: the B200 (sm_100a) kernels behind the
+ * consistent_depth test-time fine-tuning hot path.
+ *
+ * The reference (facebookresearch/consistent_depth) is pure Python/PyTorch and
+ * has NO FFI of its own; every entry point below replaces a group of ATen ops
+ * the reference dispatches from Python.  Each declaration cites the reference
+ * interface (file:line under /root/reference) it stands in for.  The Python
+ * host layer (consistent_depth_b200/*.py) binds these with ctypes and mirrors
+ * the reference's module / class / argument names.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - all data pointers are DEVICE pointers unless the name ends in _host.
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*),
+ *     never synchronises it, never allocates device memory.
+ *   - return value: 0 = ok, non-zero = error; cvd_last_error() gives a
+ *     thread-local message.  Nothing throws.
+ *   - images/activations handed over by the Python boundary are NCHW fp32 as
+ *     in the reference; the engine's internal activation layout is NHWC fp32.
+ */
+#ifndef CVD_H_
+#define CVD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVD_VERSION 100
+
+/* ---- misc ---------------------------------------------------------------- */
+int         cvd_version(void);
+const char* cvd_last_error(void);
+/* number of kernels this library has launched since load (bench.py's
+ * gpu_launches evidence). */
+long long   cvd_launch_count(void);
+
+/* ---- fused geometric-consistency loss ------------------------------------
+ * Replaces loss/consistency_loss.py:98-253 (ConsistencyLoss.__call__ +
+ * geometry_consistency_loss + weighted_mean_loss:73-89) and the
+ * utils/geometry.py primitives it calls (pixel_grid:9, pixels_to_rays:38,
+ * pixels_to_points:86, reproject_points:103, project:64, sample:201),
+ * forward AND backward (what loss.backward() does for this sub-graph,
+ * depth_fine_tuning.py:282), in one memory-bound kernel.
+ *
+ *   depth      (B,2,H,W)   predicted depths (DepthModel.forward output)
+ *   flow0/1    (B,2,H,W)   metadata["geometry_consistency"]["flows"][k]
+ *   mask0/1    (B,1,H,W)   ...["masks"][k], values 0/1
+ *   extr       (B,2,3,4)   [R|t] camera->world ; intr (B,2,4) = fx,fy,cx,cy
+ *   msum       (B,2)       sum(mask_k[b]) from cvd_mask_sums; the kernel applies
+ *                          1/max(msum,1e-6) (weighted_mean_loss, :73-89)
+ *   f_dir_host [2] or NULL mean focal length over the GLOBAL batch for
+ *                          direction k (consistency_loss.py:178); NULL =>
+ *                          computed on device from this call's intr.
+ *   B_global               divisor of the final torch.mean over pairs (:208)
+ *   acc        (B,2,2) f64 scratch, zeroed by the call
+ *   out_pair   (2,B)  f32  [0]=lambda_r*reprojection[b], [1]=lambda_b*disparity[b]
+ *                          (the reference's batch_losses dict)
+ *   out_loss   (1)    f32  sum_b(out_pair)/B_global
+ *   grad_depth (B,2,H,W) or NULL. d out_loss / d depth; zeroed by the call.
+ */
+int cvd_mask_sums(const float* mask0, const float* mask1, int B, int H, int W,
+                  float* msum, void* stream);
+
+int cvd_consistency_fwd_bwd(const float* depth,
+                            const float* flow0, const float* flow1,
+                            const float* mask0, const float* mask1,
+                            const float* extr, const float* intr,
+                            const float* msum,
+                            const float* f_dir_host,
+                            float lambda_reprojection, float lambda_view_baseline,
+                            int B, int B_global, int H, int W,
+                            double* acc, float* out_pair, float* out_loss,
+                            float* grad_depth, void* stream);
+
+/* ---- fused Adam -----------------------------------------------------------
+ * Replaces optimizer/__init__.py:16 (torch.optim.Adam) .step() as called at
+ * depth_fine_tuning.py:283, including the NaN guard of :278-280 evaluated on
+ * the device: if *loss_flag is NaN the step is skipped (no state change).
+ * step_state: 16-byte device record {int step; int skip; float step_size;
+ * float bc2_sqrt}, zero-initialised by the caller once, then owned by the kernels.
+ *   grad_scale multiplies g before use (1.0, or 1/world for rank-summed grads).
+ */
+int cvd_adam_flat(float* p, const float* g, float* m, float* v, long long n,
+                  float lr, float beta1, float beta2, float eps, float grad_scale,
+                  int* step_state /* device int[4], zero-initialised once */,
+                  const float* loss_flag /* device float[1] or NULL */,
+                  void* stream);
+
+/* lambda_parameter regulariser (loss/parameter_loss.py:13-19):
+ * out_loss[0] += lambda * sum|p - p0| ; g += lambda*sign(p-p0). */
+int cvd_param_l1(const float* p, const float* p0, long long n, float lambda,
+                 float* g_accum, float* out_loss_accum, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVD_H_ */

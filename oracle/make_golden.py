@@ -1,0 +1,171 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+    python -m oracle.make_golden
+
+Inputs are regenerated deterministically by oracle/synth.py (not stored); the
+fixtures hold only what the real reference modules produced for them:
+  consistency_*.npz : loss/consistency_loss.py ConsistencyLoss via loss/joint_loss.py JointLoss
+                      (+ autograd dL/d depth), fp32 and fp64
+  hourglass_small.npz : monodepth/mannequin_challenge/models/hourglass.py HourglassModel(3)
+                      forward (train mode) + grads of a consistency loss, BN running stats
+  adam.npz          : optimizer.create("Adam", ...) == torch.optim.Adam, 6 steps
+  finetune_steps.npz: depth_fine_tuning.py:261-283 inner loop (model -> zero_grad -> JointLoss ->
+                      backward -> step), 3 steps on one pair
+"""
+import argparse
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import ref_import, synth, hourglass_oracle as ho  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+CONSISTENCY_CASES = {
+    # name: (seed, pairs, H, W, stress, lambda_r, lambda_b)
+    "geo_b2": (11, [(0, 1), (2, 5)], 24, 32, False, 1.0, 0.1),
+    "stress_b3_oddw": (12, [(0, 2), (1, 3), (4, 6)], 20, 30, True, 1.0, 0.1),
+    "reproj_only": (13, [(0, 1)], 16, 24, False, 1.0, 0.0),
+    "disp_only": (14, [(0, 3), (1, 2)], 16, 24, False, 0.0, 1.0),
+    "midas_lambda": (15, [(3, 4)], 24, 32, False, 1.0, 1e-4),
+}
+
+
+def ref_joint_loss(lambda_r, lambda_b, dtype):
+    import loaders.video_dataset as vd
+    import loss.joint_loss as jl
+    import utils.torch_helpers as th
+    vd._dtype = dtype
+    jl._dtype = dtype
+    assert str(th._device) == "cpu", "golden vectors are generated on the CPU reference path"
+    opt = types.SimpleNamespace(lambda_view_baseline=lambda_b, lambda_reprojection=lambda_r, lambda_parameter=0)
+    return jl.JointLoss(opt)
+
+
+def to_metadata(batch, dtype):
+    t = lambda a: torch.tensor(a, dtype=dtype)
+    return {
+        "extrinsics": t(batch["extrinsics"]), "intrinsics": t(batch["intrinsics"]),
+        "geometry_consistency": {
+            "indices": torch.tensor(batch["indices"]),
+            "flows": [t(f) for f in batch["flows"]], "masks": [t(m) for m in batch["masks"]],
+        },
+    }
+
+
+def gen_consistency():
+    for name, (seed, pairs, H, W, stress, lr_, lb_) in CONSISTENCY_CASES.items():
+        batch = synth.make_pair_batch(seed, pairs, H, W, stress=stress)
+        depth = synth.synth_depth_pred(seed, len(pairs), H, W)
+        out = {}
+        for tag, dtype in (("f32", torch.float32), (("f64"), torch.float64)):
+            crit = ref_joint_loss(lr_, lb_, dtype)
+            d = torch.tensor(depth, dtype=dtype, requires_grad=True)
+            loss, meta = crit(d, to_metadata(batch, dtype))
+            loss.backward()
+            out[f"loss_{tag}"] = loss.detach().numpy()
+            out[f"reprojection_{tag}"] = meta["reprojection"].detach().numpy()
+            out[f"disparity_{tag}"] = meta["disparity"].detach().numpy()
+            out[f"grad_{tag}"] = d.grad.numpy()
+        np.savez_compressed(os.path.join(OUT, f"consistency_{name}.npz"), **out)
+        print(name, out["loss_f32"], out["loss_f64"])
+
+
+def gen_hourglass():
+    from monodepth.mannequin_challenge.models.hourglass import HourglassModel
+    seed, H, W = 21, 32, 48
+    sd = ho.mc_init_state(seed)
+    net = HourglassModel(3)
+    net.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
+    net.train()
+    batch = synth.make_pair_batch(seed, [(0, 1)], H, W)
+    images = torch.tensor(batch["images"])                                   # (1,2,3,H,W)
+    pred, _ = net.forward(images.reshape(-1, 3, H, W))                       # adapter: mannequin_challenge_model.py:52-69
+    depth = torch.exp(pred.reshape(1, 2, H, W))
+    crit = ref_joint_loss(1.0, 0.1, torch.float32)
+    loss, meta = crit(depth, to_metadata(batch, torch.float32))
+    loss.backward()
+    out = {"log_depth": pred.detach().numpy(), "depth": depth.detach().numpy(), "loss": loss.detach().numpy()}
+    names, norms = [], []
+    for k, p in net.named_parameters():
+        if p.grad is None:
+            continue
+        names.append(k); norms.append(float(p.grad.double().norm()))
+    out["grad_names"] = np.array(names); out["grad_norms"] = np.array(norms)
+    for k in ("seq.0.weight", "seq.1.weight", "seq.1.bias", "pred_layer.weight", "pred_layer.bias",
+              "seq.3.list.1.0.convs.3.3.weight", "seq.3.list.0.1.convs.0.0.weight",
+              "seq.3.list.0.3.list.0.3.list.1.3.list.0.0.convs.2.3.weight"):
+        out["grad::" + k] = dict(net.named_parameters())[k].grad.numpy()
+    st = net.state_dict()
+    for k in ("seq.1.running_mean", "seq.1.running_var", "seq.3.list.1.0.convs.3.4.running_var",
+              "seq.3.list.0.5.convs.0.1.running_mean"):
+        out["buf::" + k] = st[k].numpy()
+    np.savez_compressed(os.path.join(OUT, "hourglass_small.npz"), **out)
+    print("hourglass loss", out["loss"], "ngrads", len(names))
+
+
+def gen_adam():
+    import optimizer
+    p0 = synth.normal(31, 1, (1003,), 0.1)
+    p = torch.nn.Parameter(torch.tensor(p0.copy()))
+    opt = optimizer.create("Adam", [p], 4e-4, betas=(0.9, 0.999))
+    out = {}
+    for t in range(6):
+        g = synth.normal(31, 10 + t, (1003,), 10.0 ** (-t))      # widely varying gradient scales
+        p.grad = torch.tensor(g)
+        opt.step()
+        out[f"p_{t}"] = p.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "adam.npz"), **out)
+
+
+def gen_finetune():
+    import optimizer
+    from monodepth.mannequin_challenge.models.hourglass import HourglassModel
+    seed, H, W, steps = 41, 32, 48, 3
+    sd = ho.mc_init_state(seed)
+    net = HourglassModel(3)
+    net.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
+    net.train()
+    batch = synth.make_pair_batch(seed, [(0, 2)], H, W)
+    images = torch.tensor(batch["images"])
+    crit = ref_joint_loss(1.0, 0.1, torch.float32)
+    opt = optimizer.create("Adam", net.parameters(), 4e-4, betas=(0.9, 0.999))
+    meta = to_metadata(batch, torch.float32)
+    losses = []
+    for _ in range(steps):
+        pred, _ = net.forward(images.reshape(-1, 3, H, W))
+        depth = torch.exp(pred.reshape(1, 2, H, W))
+        opt.zero_grad()
+        loss, _m = crit(depth, meta)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss[0]))
+    with torch.no_grad():
+        pred, _ = net.forward(images.reshape(-1, 3, H, W))
+    out = {"losses": np.array(losses), "final_depth": torch.exp(pred.reshape(1, 2, H, W)).numpy(),
+           "pred_layer.bias": net.state_dict()["pred_layer.bias"].numpy(),
+           "seq.0.weight": net.state_dict()["seq.0.weight"].numpy()}
+    np.savez_compressed(os.path.join(OUT, "finetune_steps.npz"), **out)
+    print("finetune losses", losses)
+
+
+def main():
+    argparse.ArgumentParser(description=__doc__).parse_args()
+    ref_import.setup()
+    torch.manual_seed(0)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    os.makedirs(OUT, exist_ok=True)
+    gen_consistency()
+    gen_adam()
+    gen_hourglass()
+    gen_finetune()
+
+
+if __name__ == "__main__":
+    main()

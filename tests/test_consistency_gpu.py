@@ -1,0 +1,125 @@
+"""GPU: fused reproject+consistency kernel vs the oracle and the reference-generated goldens.
+
+Tolerances (fp32 kernel): loss / per-pair losses rel 1e-5 vs the fp32 reference and vs the
+fp64 reference; dL/d depth max-abs error <= 1e-4 of the gradient's max magnitude (scatter
+atomics reorder fp32 sums) — SURVEY.md §8(d) parity tolerances.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth, consistency_oracle as co
+from oracle.make_golden import CONSISTENCY_CASES
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(depth, batch, lam_r, lam_b, **kw):
+    from consistent_depth_b200.utils.geometry import fused_consistency
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.tensor(a, device=dev)
+    loss, pair, grad = fused_consistency(t(depth), [t(f) for f in batch["flows"]], [t(m) for m in batch["masks"]],
+                                         t(batch["extrinsics"]), t(batch["intrinsics"]), lam_r, lam_b, **kw)
+    torch.cuda.synchronize()
+    return loss.cpu().numpy(), pair.cpu().numpy(), None if grad is None else grad.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", sorted(CONSISTENCY_CASES))
+def test_matches_reference_golden(name, golden_dir):
+    seed, pairs, H, W, stress, lam_r, lam_b = CONSISTENCY_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"consistency_{name}.npz"))
+    batch = synth.make_pair_batch(seed, pairs, H, W, stress=stress)
+    depth = synth.synth_depth_pred(seed, len(pairs), H, W)
+    loss, pair, grad = _run(depth, batch, lam_r, lam_b)
+    for tag in ("f32", "f64"):
+        np.testing.assert_allclose(loss, g[f"loss_{tag}"], rtol=1e-5)
+        np.testing.assert_allclose(pair[0], g[f"reprojection_{tag}"], rtol=1e-5, atol=1e-12)
+        np.testing.assert_allclose(pair[1], g[f"disparity_{tag}"], rtol=1e-5, atol=1e-12)
+    gref = g["grad_f64"]
+    assert np.abs(grad - gref).max() <= 1e-4 * np.abs(gref).max()
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 16, 16), (4, 224, 384), (3, 33, 47), (2, 96, 130)])
+def test_matches_oracle_sizes(B, H, W):
+    pairs = [(i, i + 1 + (i % 3)) for i in range(B)]
+    batch = synth.make_pair_batch(100 + B, pairs, H, W)
+    depth = synth.synth_depth_pred(100 + B, B, H, W)
+    loss, pair, grad = _run(depth, batch, 1.0, 0.1)
+    rl, rm, rg = co.consistency_loss_and_grad(depth, batch, 1.0, 0.1, dtype=torch.float64)
+    np.testing.assert_allclose(loss, rl, rtol=1e-5)
+    np.testing.assert_allclose(pair[0], rm["reprojection"], rtol=1e-5)
+    np.testing.assert_allclose(pair[1], rm["disparity"], rtol=1e-5)
+    assert np.abs(grad - rg).max() <= 1e-4 * np.abs(rg).max()
+
+
+def test_forward_only_and_global_batch_scalars():
+    B, H, W = 2, 24, 32
+    batch = synth.make_pair_batch(7, [(0, 1), (2, 4)], H, W)
+    depth = synth.synth_depth_pred(7, B, H, W)
+    l0, p0, g0 = _run(depth, batch, 1.0, 0.1)
+    l1, p1, g1 = _run(depth, batch, 1.0, 0.1, want_grad=False)
+    assert g1 is None and np.allclose(l0, l1, rtol=1e-6) and np.allclose(p0, p1, rtol=1e-6)
+    # multi-GPU hooks: B_global rescales mean and gradient; f_dir overrides the batch-mean focal length
+    l2, p2, g2 = _run(depth, batch, 1.0, 0.1, B_global=8)
+    np.testing.assert_allclose(l2 * 4, l0, rtol=1e-5)
+    np.testing.assert_allclose(g2 * 4, g0, rtol=1e-4, atol=1e-9)
+    f = float(np.mean(batch["intrinsics"][:, 0, :2]))
+    l3, p3, g3 = _run(depth, batch, 1.0, 0.1, f_dir=(2 * f, 2 * f))
+    np.testing.assert_allclose(p3[1], 2 * p0[1], rtol=1e-5)
+    np.testing.assert_allclose(p3[0], p0[0], rtol=1e-6)
+
+
+def test_nan_propagates_like_reference():
+    B, H, W = 1, 16, 16
+    batch = synth.make_pair_batch(9, [(0, 1)], H, W)
+    depth = synth.synth_depth_pred(9, B, H, W)
+    depth[0, 0, 3, 3] = np.nan
+    loss, pair, grad = _run(depth, batch, 1.0, 0.1)
+    assert np.isnan(loss).all()
+
+
+def test_size_independent_properties_full_size():
+    """At BASELINE config-2 size: (i) zero masks => zero loss and zero grad; (ii) identity pose +
+    zero flow + equal depths => zero loss; (iii) loss is linear in the lambdas."""
+    B, H, W = 4, 224, 384
+    pairs = [(0, 1), (1, 3), (2, 6), (5, 9)]
+    batch = synth.make_pair_batch(55, pairs, H, W)
+    depth = synth.synth_depth_pred(55, B, H, W)
+    zb = dict(batch); zb["masks"] = [np.zeros_like(m) for m in batch["masks"]]
+    l, p, g = _run(depth, zb, 1.0, 0.1)
+    assert float(l) == 0.0 and np.abs(g).max() == 0.0
+    ib = dict(batch)
+    eye = np.zeros((B, 2, 3, 4), np.float32); eye[..., :3] = np.eye(3)
+    ib["extrinsics"] = eye; ib["flows"] = [np.zeros_like(f) for f in batch["flows"]]
+    same = np.repeat(depth[:, :1], 2, axis=1)
+    l, p, g = _run(same, ib, 1.0, 0.1)
+    assert abs(float(l)) < 1e-4
+    la, pa, _ = _run(depth, batch, 1.0, 0.1)
+    lb, pb, _ = _run(depth, batch, 2.0, 0.3)
+    np.testing.assert_allclose(pb[0], 2 * pa[0], rtol=1e-5)
+    np.testing.assert_allclose(pb[1], 3 * pa[1], rtol=1e-5)
+
+
+def test_module_api_matches_reference_signature(golden_dir):
+    """JointLoss(opt)(depths, metadata) -> (loss (1,), dict) with autograd into depths, like loss/joint_loss.py."""
+    import types
+    from consistent_depth_b200.loss.joint_loss import JointLoss
+    name = "geo_b2"
+    seed, pairs, H, W, stress, lam_r, lam_b = CONSISTENCY_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"consistency_{name}.npz"))
+    batch = synth.make_pair_batch(seed, pairs, H, W, stress=stress)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.tensor(a, device=dev)
+    meta = {"extrinsics": t(batch["extrinsics"]), "intrinsics": t(batch["intrinsics"]),
+            "geometry_consistency": {"indices": t(batch["indices"]), "flows": [t(f) for f in batch["flows"]],
+                                     "masks": [t(m) for m in batch["masks"]]}}
+    opt = types.SimpleNamespace(lambda_view_baseline=lam_b, lambda_reprojection=lam_r, lambda_parameter=0)
+    depth = t(synth.synth_depth_pred(seed, len(pairs), H, W)).requires_grad_(True)
+    loss, meta_out = JointLoss(opt)(depth, meta)
+    assert loss.shape == (1,) and set(meta_out) == {"reprojection", "disparity"}
+    loss.backward()
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), g["loss_f32"], rtol=1e-5)
+    gref = g["grad_f64"]
+    assert np.abs(depth.grad.cpu().numpy() - gref).max() <= 1e-4 * np.abs(gref).max()
