@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcvd_sm100.so")
+LIB_PATH = os.environ.get("CVD_LIB", os.path.join(_HERE, "lib", "libcvd_sm100.so"))
 
 
 class CvdError(RuntimeError):
@@ -42,6 +42,7 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.cvd_last_error.restype = C.c_char_p
         _lib.cvd_launch_count.restype = C.c_longlong
+        _lib.cvd_consistency_workspace_bytes.restype = C.c_size_t
     return _lib
 
 

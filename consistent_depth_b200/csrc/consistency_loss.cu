@@ -15,9 +15,12 @@
 // Everything else (pixel grid, rays, points, reprojected points, projected
 // pixels, sampled z, per-pixel distances) lives in registers.
 //
-// Work decomposition: grid = (pixel-quads / 256, B).  A thread owns 4
-// x-adjacent pixels and handles BOTH directions (ref=0->tgt=1 and ref=1->tgt=0)
-// so the eight 128-bit streaming loads are all in flight before any math.
+// Work decomposition: grid = (pixels / 1024, B).  A block owns 1024 consecutive
+// pixels; a thread owns 4 of them strided by the block size (so a warp's lanes
+// are x-adjacent pixels: coalesced 128 B loads AND spatially coherent scatter
+// REDs that merge into few L2 sector requests) and handles BOTH directions, so
+// 32 independent loads are in flight per thread before any math.  Per
+// pixel-direction the math is ~80 instructions (rcp/rsqrt via MUFU approx).
 // The bilinear gather reads the other frame's depth plane through the
 // read-only path (it is L1/L2 resident: flow is spatially coherent); the
 // matching backward scatter uses fire-and-forget fp32 REDs that resolve in L2.
@@ -25,186 +28,210 @@
 
 namespace {
 
+// Per pair-direction constants, computed once per block (in double) and broadcast from smem.
+// Q = d * (M ray) + c with M = R_t^T R_r, c = R_t^T (t_r - t_t): the reference's
+// baddbmm+bmm chain (geometry.py:121-127) collapsed to 9 FMAs per pixel.
 struct DirConst {
-  float Rr[9], tr[3], tt[3], Rt[9];
-  float fx, fy, cx, cy;       // reference-frame intrinsics
+  float M[9], c[3];
+  float ifx, ify, cx, cy;     // reference-frame intrinsics (1/fx, 1/fy)
   float fxt, fyt, cxt, cyt;   // target-frame intrinsics
   float cr, cd;               // gradient coefficients incl. 1/(2 B_global) and 1/mask_sum
 };
 
 struct PairConst { DirConst d[2]; };
 
-__device__ __forceinline__ void pixel_term(
-    const DirConst& c, const float* __restrict__ depth_t, float* __restrict__ grad_t,
-    float x, float y, float d, float fu, float fv, float mk,
-    int H, int W, float Wm1, float Hm1, bool do_r, bool do_d, bool want_grad,
-    float& acc_r, float& acc_d, float& g_direct)
-{
-  // pixels_to_rays (geometry.py:38-61): ((x-cx)/fx, -(y-cy)/fy, -1)
-  const float rx = (x - c.cx) / c.fx;
-  const float ry = -(y - c.cy) / c.fy;
-  // pixels_to_points (:86-100)
-  const float px = rx * d, py = ry * d, pz = -d;
-  // reproject_points (:103-128): world = t_r + R_r p ; cam_tgt = R_t^T (world - t_t)
-  const float wx = c.tr[0] + (c.Rr[0] * px + c.Rr[1] * py + c.Rr[2] * pz);
-  const float wy = c.tr[1] + (c.Rr[3] * px + c.Rr[4] * py + c.Rr[5] * pz);
-  const float wz = c.tr[2] + (c.Rr[6] * px + c.Rr[7] * py + c.Rr[8] * pz);
-  const float dx = wx - c.tt[0], dy = wy - c.tt[1], dz = wz - c.tt[2];
-  const float Qx = c.Rt[0] * dx + c.Rt[3] * dy + c.Rt[6] * dz;
-  const float Qy = c.Rt[1] * dx + c.Rt[4] * dy + c.Rt[7] * dz;
-  const float Qz = c.Rt[2] * dx + c.Rt[5] * dy + c.Rt[8] * dz;
-  // dQ/dd = R_t^T R_r ray
-  const float ax = c.Rr[0] * rx + c.Rr[1] * ry - c.Rr[2];
-  const float ay = c.Rr[3] * rx + c.Rr[4] * ry - c.Rr[5];
-  const float az = c.Rr[6] * rx + c.Rr[7] * ry - c.Rr[8];
-  const float mx = c.Rt[0] * ax + c.Rt[3] * ay + c.Rt[6] * az;
-  const float my = c.Rt[1] * ax + c.Rt[4] * ay + c.Rt[7] * az;
-  const float mz = c.Rt[2] * ax + c.Rt[5] * ay + c.Rt[8] * az;
+__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-  const float tx = x + fu, ty = y + fv;   // matched_pixels_tgt = pixels_ref + flow (:165)
-  const float inv_nz = 1.0f / (-Qz);
+#ifndef CVD_LOSS_PIX
+#define CVD_LOSS_PIX 4
+#endif
+#ifndef CVD_LOSS_MINB
+#define CVD_LOSS_MINB 3
+#endif
+constexpr int PIX = CVD_LOSS_PIX;   // pixels per thread, strided by the block size (lane <-> adjacent pixels)
+constexpr int LOSS_THREADS = 256;
+
+template <bool want_grad, bool do_r, bool do_d>
+__device__ __forceinline__ float pixel_term(
+    const DirConst& c, const float* __restrict__ depth_t, float* __restrict__ grad_t, int plane_off,
+    float x, float y, float d, float fu, float fv, float mk,
+    int W, int Wm1i, int Hm1i, float sxs, float sys,
+    float& acc_r, float& acc_d)
+{
+  // pixels_to_rays (geometry.py:38-61): ((x-cx)/fx, -(y-cy)/fy, -1) ; m = M ray
+  const float rx = (x - c.cx) * c.ifx;
+  const float ry = (c.cy - y) * c.ify;
+  const float mx = fmaf(c.M[0], rx, fmaf(c.M[1], ry, -c.M[2]));
+  const float my = fmaf(c.M[3], rx, fmaf(c.M[4], ry, -c.M[5]));
+  const float mz = fmaf(c.M[6], rx, fmaf(c.M[7], ry, -c.M[8]));
+  // pixels_to_points + reproject_points (:86-128)
+  const float Qx = fmaf(d, mx, c.c[0]), Qy = fmaf(d, my, c.c[1]), Qz = fmaf(d, mz, c.c[2]);
+  const float rq = rcp_fast(Qz);                       // 1/Qz
+  const float a = Qx * rq, b = Qy * rq;
+  const float tx = x + fu, ty = y + fv;                // matched_pixels_tgt (:165)
   float g = 0.f;
 
   if (do_r) {
-    // project (:64-83): u = (Qx/-Qz) fx' + cx' ; v = -(Qy/-Qz) fy' + cy'
-    const float u = (Qx * inv_nz) * c.fxt + c.cxt;
-    const float v = -((Qy * inv_nz) * c.fyt) + c.cyt;
-    const float ex = u - tx, ey = v - ty;
-    const float dist = sqrtf(ex * ex + ey * ey);      // torch.norm(dim=1) (:170)
-    acc_r += mk * dist;
-    if (want_grad && dist > 0.f) {                    // norm subgradient 0 at 0
-      const float iq2 = inv_nz * inv_nz;              // 1/Qz^2
-      const float du = -c.fxt * (mx * Qz - Qx * mz) * iq2;
-      const float dv =  c.fyt * (my * Qz - Qy * mz) * iq2;
-      g += c.cr * mk * ((ex * du + ey * dv) / dist);
+    // project (:64-83): u = -fx' Qx/Qz + cx' ; v = +fy' Qy/Qz + cy'
+    const float ex = fmaf(-c.fxt, a, c.cxt) - tx;
+    const float ey = fmaf(c.fyt, b, c.cyt) - ty;
+    const float d2 = fmaf(ex, ex, ey * ey);
+    const float rs = rsqrt_fast(d2);
+    const float dist = d2 > 0.f ? d2 * rs : d2;       // torch.norm (:170); d2 itself carries NaN/0
+    acc_r = fmaf(mk, dist, acc_r);
+    if (want_grad) {
+      const float du = -c.fxt * (mx - a * mz);         // * rq below
+      const float dv = c.fyt * (my - b * mz);
+      const float t = (ex * du + ey * dv) * rq * rs;   // d dist / d d
+      g = d2 > 0.f ? c.cr * mk * t : 0.f;              // norm subgradient 0 at 0
     }
   }
   if (do_d) {
-    // sample (:201-208): grid = 2 uv/(W-1,H-1) - 1 ; grid_sample unnormalise
-    // (align_corners=False): ((g+1)*size-1)/2 ; border clamp ; bilinear.
-    float ix = ((2.0f * tx / Wm1 - 1.0f) + 1.0f) * (float)W;
-    ix = (ix - 1.0f) * 0.5f;
-    float iy = ((2.0f * ty / Hm1 - 1.0f) + 1.0f) * (float)H;
-    iy = (iy - 1.0f) * 0.5f;
-    ix = fminf(fmaxf(ix, 0.f), (float)(W - 1));
-    iy = fminf(fmaxf(iy, 0.f), (float)(H - 1));
+    // sample (:201-208): grid_sample(bilinear, border, align_corners=False) at
+    // ix = tx W/(W-1) - 0.5 (the (2uv/(W-1)-1 -> ((g+1)W-1)/2) chain folded to one FMA)
+    float ix = fmaf(tx, sxs, -0.5f), iy = fmaf(ty, sys, -0.5f);
+    ix = fminf(fmaxf(ix, 0.f), (float)Wm1i);
+    iy = fminf(fmaxf(iy, 0.f), (float)Hm1i);
     const float x0f = floorf(ix), y0f = floorf(iy);
+    const float wx1 = ix - x0f, wy1 = iy - y0f;
+    const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
     const int x0 = (int)x0f, y0 = (int)y0f;
-    const int x1 = x0 + 1, y1 = y0 + 1;
-    const float wx1 = ix - x0f, wx0 = (x0f + 1.0f) - ix;
-    const float wy1 = iy - y0f, wy0 = (y0f + 1.0f) - iy;
-    const bool xin = x1 < W, yin = y1 < H;           // x0,y0 always in bounds after clamp
+    // border taps: the +1 neighbour is clamped; its weight is exactly 0 there
+    const int i00 = y0 * W + x0 + plane_off;     // 32-bit element index into the whole tensor
+    const int i10 = i00 + (x0 < Wm1i ? 1 : 0);
+    const int i01 = i00 + (y0 < Hm1i ? W : 0);
+    const int i11 = i01 + (i10 - i00);
     const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
-    const int i00 = y0 * W + x0;
-    float zs = w00 * __ldg(depth_t + i00);
-    if (xin) zs += w10 * __ldg(depth_t + i00 + 1);
-    if (yin) zs += w01 * __ldg(depth_t + i00 + W);
-    if (xin && yin) zs += w11 * __ldg(depth_t + i00 + W + 1);
-    const float zw = -zs;                             // target points' z = -depth
-    const float s = 1.0f / Qz - 1.0f / zw;            // disp_diff (:188-189)
-    acc_d += mk * fabsf(s);
+    const float d00 = __ldg(depth_t + i00), d10 = __ldg(depth_t + i10);
+    const float d01 = __ldg(depth_t + i01), d11 = __ldg(depth_t + i11);
+    const float zs = fmaf(w00, d00, fmaf(w10, d10, fmaf(w01, d01, w11 * d11)));   // = -z_w
+    const float rz = rcp_fast(zs);                     // -1/z_w
+    const float s = rq + rz;                           // 1/Qz - 1/z_w (:188-189)
+    acc_d = fmaf(mk, fabsf(s), acc_d);
     if (want_grad) {
       const float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
       const float k0 = c.cd * mk * sg;
-      g += k0 * (-mz * (inv_nz * inv_nz));
-      const float k1 = -k0 / (zw * zw);               // d|s|/d depth_tgt[tap] = -sg * wt / zw^2
-      if (k1 != 0.f) {
-        atomicAdd(grad_t + i00, k1 * w00);
-        if (xin) atomicAdd(grad_t + i00 + 1, k1 * w10);
-        if (yin) atomicAdd(grad_t + i00 + W, k1 * w01);
-        if (xin && yin) atomicAdd(grad_t + i00 + W + 1, k1 * w11);
-      }
+      g = fmaf(k0, -mz * rq * rq, g);
+      const float k1 = -k0 * rz * rz;                  // d|s|/d depth_tgt[tap] = -sg wt / z_w^2
+      const float v00 = k1 * w00, v10 = k1 * w10, v01 = k1 * w01, v11 = k1 * w11;
+      if (v00 != 0.f) atomicAdd(grad_t + i00, v00);    // masked-out pixels and zero-weight border taps skip the RED
+      if (v10 != 0.f) atomicAdd(grad_t + i10, v10);
+      if (v01 != 0.f) atomicAdd(grad_t + i01, v01);
+      if (v11 != 0.f) atomicAdd(grad_t + i11, v11);
     }
   }
-  g_direct = g;
+  return g;
 }
 
-template <int VEC>
-__global__ void __launch_bounds__(256)
+// One thread per (pair, direction): collapse the poses to M = R_t^T R_r, c = R_t^T (t_r - t_t) in
+// double, fold 1/(2 B_global), 1/max(sum(mask),1e-6) and the batch-mean focal length into the
+// gradient coefficients.  Runs once per call (B*2 threads), so the main kernel has no serial prologue.
+__global__ void consistency_setup(const float* __restrict__ extr, const float* __restrict__ intr,
+                                  const float* __restrict__ msum, float f0, float f1, int f_given,
+                                  float lam_r, float lam_b, int B, int B_global, PairConst* __restrict__ consts)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * B) return;
+  const int b = i >> 1, k = i & 1, t = 1 - k;
+  DirConst c;
+  const float* Er = extr + ((size_t)b * 2 + k) * 12;
+  const float* Et = extr + ((size_t)b * 2 + t) * 12;
+  double dt[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) dt[a] = (double)Er[a * 4 + 3] - (double)Et[a * 4 + 3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {          // row a of R_t^T = column a of R_t
+    double ca = 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double m = 0.0;
+#pragma unroll
+      for (int l = 0; l < 3; ++l) m += (double)Et[l * 4 + a] * (double)Er[l * 4 + j];
+      c.M[a * 3 + j] = (float)m;
+      ca += (double)Et[j * 4 + a] * dt[j];
+    }
+    c.c[a] = (float)ca;
+  }
+  const float* Ir = intr + ((size_t)b * 2 + k) * 4;
+  const float* It = intr + ((size_t)b * 2 + t) * 4;
+  c.ifx = 1.0f / Ir[0]; c.ify = 1.0f / Ir[1]; c.cx = Ir[2]; c.cy = Ir[3];
+  c.fxt = It[0]; c.fyt = It[1]; c.cxt = It[2]; c.cyt = It[3];
+  float f = k ? f1 : f0;
+  if (!f_given) {          // f = mean(focal_length(intrinsics_ref)) over the batch (:178)
+    float sacc = 0.f;
+    for (int bb = 0; bb < B; ++bb) { const float* I = intr + ((size_t)bb * 2 + k) * 4; sacc += I[0]; sacc += I[1]; }
+    f = sacc / (float)(2 * B);
+  }
+  const float inv = 1.0f / fmaxf(msum[b * 2 + k], 1e-6f);   // weighted_mean_loss eps (:73)
+  const float half_over_B = 0.5f / (float)B_global;
+  c.cr = lam_r * half_over_B * inv;
+  c.cd = lam_b * f * half_over_B * inv;
+  consts[b].d[k] = c;
+}
+
+template <bool GRAD, bool DO_R, bool DO_D, bool FULL>
+__global__ void __launch_bounds__(LOSS_THREADS, CVD_LOSS_MINB)
 consistency_kernel(const float* __restrict__ depth,
                    const float* __restrict__ flow0, const float* __restrict__ flow1,
                    const float* __restrict__ mask0, const float* __restrict__ mask1,
-                   const float* __restrict__ extr, const float* __restrict__ intr,
-                   const float* __restrict__ msum,
-                   float f0, float f1, int f_given,
-                   float lam_r, float lam_b, int B, int B_global, int H, int W,
+                   const PairConst* __restrict__ consts, int H, int W,
                    double* __restrict__ acc, float* __restrict__ grad)
 {
   __shared__ PairConst pc;
-  __shared__ float red[8][4];
+  __shared__ float red[LOSS_THREADS / 32][4];
   const int b = blockIdx.y;
   const int HW = H * W;
-  const bool want_grad = grad != nullptr;
 
-  if (threadIdx.x < 2) {
-    const int k = threadIdx.x, t = 1 - k;
-    DirConst& c = pc.d[k];
-    const float* Er = extr + ((size_t)b * 2 + k) * 12;
-    const float* Et = extr + ((size_t)b * 2 + t) * 12;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) { c.Rr[i * 3 + j] = Er[i * 4 + j]; c.Rt[i * 3 + j] = Et[i * 4 + j]; }
-      c.tr[i] = Er[i * 4 + 3]; c.tt[i] = Et[i * 4 + 3];
-    }
-    const float* Ir = intr + ((size_t)b * 2 + k) * 4;
-    const float* It = intr + ((size_t)b * 2 + t) * 4;
-    c.fx = Ir[0]; c.fy = Ir[1]; c.cx = Ir[2]; c.cy = Ir[3];
-    c.fxt = It[0]; c.fyt = It[1]; c.cxt = It[2]; c.cyt = It[3];
-    float f = k ? f1 : f0;
-    if (!f_given) {          // f = mean(focal_length(intrinsics_ref)) over the batch (:178)
-      float sacc = 0.f;
-      for (int bb = 0; bb < B; ++bb) { const float* I = intr + ((size_t)bb * 2 + k) * 4; sacc += I[0]; sacc += I[1]; }
-      f = sacc / (float)(2 * B);
-    }
-    const float inv = 1.0f / fmaxf(msum[b * 2 + k], 1e-6f);   // weighted_mean_loss eps (:73)
-    const float half_over_B = 0.5f / (float)B_global;
-    c.cr = lam_r * half_over_B * inv;
-    c.cd = lam_b * f * half_over_B * inv;
+  {   // per-pair constants were prepared by consistency_setup; stage them in smem (broadcast reads)
+    const float* src = reinterpret_cast<const float*>(consts + b);
+    float* dst = reinterpret_cast<float*>(&pc);
+    for (int i = threadIdx.x; i < (int)(sizeof(PairConst) / 4); i += LOSS_THREADS) dst[i] = __ldg(src + i);
   }
   __syncthreads();
 
-  const bool do_r = lam_r > 0.f, do_d = lam_b > 0.f;   // (:169,176)
-  const float Wm1 = (float)(W - 1), Hm1 = (float)(H - 1);
+  const float sxs = (float)W / (float)(W - 1), sys = (float)H / (float)(H - 1);
+  const float invW = 1.0f / (float)W;
   float a_r[2] = {0.f, 0.f}, a_d[2] = {0.f, 0.f};
 
-  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long p0 = q * VEC;
-  if (p0 < HW) {
-    const size_t pl = (size_t)b * 2 * HW;              // plane base of pair b (2 planes of HW)
-    float dv[2][VEC], fu[2][VEC], fv[2][VEC], mk[2][VEC];
-    if constexpr (VEC == 4) {
-      auto ld4 = [](const float* p, float (&a)[VEC]) { float4 t = ldg_stream4(p); a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; };
-      ld4(depth + pl + p0, dv[0]);       ld4(depth + pl + HW + p0, dv[1]);
-      ld4(flow0 + pl + p0, fu[0]);       ld4(flow0 + pl + HW + p0, fv[0]);
-      ld4(flow1 + pl + p0, fu[1]);       ld4(flow1 + pl + HW + p0, fv[1]);
-      ld4(mask0 + (size_t)b * HW + p0, mk[0]);
-      ld4(mask1 + (size_t)b * HW + p0, mk[1]);
-    } else {
-      dv[0][0] = depth[pl + p0]; dv[1][0] = depth[pl + HW + p0];
-      fu[0][0] = flow0[pl + p0]; fv[0][0] = flow0[pl + HW + p0];
-      fu[1][0] = flow1[pl + p0]; fv[1][0] = flow1[pl + HW + p0];
-      mk[0][0] = mask0[(size_t)b * HW + p0]; mk[1][0] = mask1[(size_t)b * HW + p0];
-    }
-    const int y = (int)(p0 / W), x0 = (int)(p0 - (long long)y * W);
+  const int base = blockIdx.x * (LOSS_THREADS * PIX) + threadIdx.x;
+  // per-array pointers for this thread's first pixel; the other PIX-1 are at constant strides
+  const float* pd0 = depth + (size_t)b * 2 * HW + base;
+  const float* pd1 = pd0 + HW;
+  const float* pf0u = flow0 + (size_t)b * 2 * HW + base;
+  const float* pf0v = pf0u + HW;
+  const float* pf1u = flow1 + (size_t)b * 2 * HW + base;
+  const float* pf1v = pf1u + HW;
+  const float* pm0 = mask0 + (size_t)b * HW + base;
+  const float* pm1 = mask1 + (size_t)b * HW + base;
+  float dv[2][PIX], fu[2][PIX], fv[2][PIX], mk[2][PIX];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const float* depth_t = depth + pl + (size_t)(1 - k) * HW;
-      float* grad_t = want_grad ? grad + pl + (size_t)(1 - k) * HW : nullptr;
-      float gd[VEC];
+  for (int j = 0; j < PIX; ++j) {                      // 32 independent coalesced loads in flight
+    const int o = j * LOSS_THREADS;
+    const bool ok = FULL || (base + o < HW);
+    dv[0][j] = ok ? __ldcs(pd0 + o) : 1.f;   dv[1][j] = ok ? __ldcs(pd1 + o) : 1.f;
+    fu[0][j] = ok ? __ldcs(pf0u + o) : 0.f;  fv[0][j] = ok ? __ldcs(pf0v + o) : 0.f;
+    fu[1][j] = ok ? __ldcs(pf1u + o) : 0.f;  fv[1][j] = ok ? __ldcs(pf1v + o) : 0.f;
+    mk[0][j] = ok ? __ldcs(pm0 + o) : 0.f;   mk[1][j] = ok ? __ldcs(pm1 + o) : 0.f;
+  }
+  float* gpl = GRAD ? grad + (size_t)b * 2 * HW : nullptr;
+  float* gd0 = GRAD ? gpl + base : nullptr;            // direct-term targets, constant strides per j
+  float* gd1 = GRAD ? gd0 + HW : nullptr;
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        pixel_term(pc.d[k], depth_t, grad_t, (float)(x0 + j), (float)y,
-                   dv[k][j], fu[k][j], fv[k][j], mk[k][j], H, W, Wm1, Hm1,
-                   do_r, do_d, want_grad, a_r[k], a_d[k], gd[j]);
-      }
-      if (want_grad) {
-        float* gp = grad + pl + (size_t)k * HW + p0;
-        if constexpr (VEC == 4) {
-          atomicAdd(reinterpret_cast<float4*>(gp), make_float4(gd[0], gd[1], gd[2], gd[3]));
-        } else {
-          atomicAdd(gp, gd[0]);
-        }
+  for (int j = 0; j < PIX; ++j) {
+    const int p = base + j * LOSS_THREADS;
+    if (FULL || p < HW) {
+      // (y, x) of the flattened index without an integer divide (exact for HW < 2^22, checked on host)
+      int y = __float2int_rd(((float)p + 0.5f) * invW);
+      int x = p - y * W;
+      if (x < 0) { x += W; --y; } else if (x >= W) { x -= W; ++y; }
+      const float xf = (float)x, yf = (float)y;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float g = pixel_term<GRAD, DO_R, DO_D>(pc.d[k], depth, grad, (b * 2 + 1 - k) * HW, xf, yf,
+                                                     dv[k][j], fu[k][j], fv[k][j], mk[k][j],
+                                                     W, W - 1, H - 1, sxs, sys, a_r[k], a_d[k]);
+        if (GRAD) atomicAdd((k ? gd1 : gd0) + j * LOSS_THREADS, g);
       }
     }
   }
@@ -217,7 +244,7 @@ consistency_kernel(const float* __restrict__ depth,
   if (threadIdx.x < 4) {
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += (double)red[w][threadIdx.x];
+    for (int w = 0; w < LOSS_THREADS / 32; ++w) s += (double)red[w][threadIdx.x];
     atomicAdd(acc + (size_t)b * 4 + threadIdx.x, s);
   }
 }
@@ -310,6 +337,11 @@ extern "C" int cvd_mask_sums(const float* mask0, const float* mask1, int B, int 
   return 0;
 }
 
+extern "C" size_t cvd_consistency_workspace_bytes(int B)
+{
+  return B > 0 ? (size_t)B * (4 * sizeof(double) + sizeof(PairConst)) : 0;
+}
+
 extern "C" int cvd_consistency_fwd_bwd(const float* depth,
                                        const float* flow0, const float* flow1,
                                        const float* mask0, const float* mask1,
@@ -317,14 +349,17 @@ extern "C" int cvd_consistency_fwd_bwd(const float* depth,
                                        const float* msum, const float* f_dir_host,
                                        float lam_r, float lam_b,
                                        int B, int B_global, int H, int W,
-                                       double* acc, float* out_pair, float* out_loss,
+                                       void* workspace, float* out_pair, float* out_loss,
                                        float* grad_depth, void* stream)
 {
-  CVD_CHECK_ARG(depth && flow0 && flow1 && mask0 && mask1 && extr && intr && msum && acc && out_pair && out_loss,
+  CVD_CHECK_ARG(depth && flow0 && flow1 && mask0 && mask1 && extr && intr && msum && workspace && out_pair && out_loss,
                 "cvd_consistency_fwd_bwd: null pointer");
+  CVD_CHECK_ARG(((uintptr_t)workspace & 15) == 0, "cvd_consistency_fwd_bwd: workspace must be 16-byte aligned");
+  double* acc = reinterpret_cast<double*>(workspace);
   CVD_CHECK_ARG(B > 0 && B <= 65535 && H > 1 && W > 1 && B_global >= B,
                 "cvd_consistency_fwd_bwd: bad shape B=%d B_global=%d H=%d W=%d", B, B_global, H, W);
-  CVD_CHECK_ARG((long long)H * W < (1ll << 30), "cvd_consistency_fwd_bwd: image too large");
+  CVD_CHECK_ARG((long long)H * W < (1ll << 22), "cvd_consistency_fwd_bwd: image larger than 4 Mpx not supported");
+  CVD_CHECK_ARG(2ll * B * H * W < (1ll << 31), "cvd_consistency_fwd_bwd: B*2*H*W must stay below 2^31 elements per call");
   cudaStream_t st = (cudaStream_t)stream;
   const long long HW = (long long)H * W;
   cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(double) * 4 * B, st);
@@ -332,18 +367,19 @@ extern "C" int cvd_consistency_fwd_bwd(const float* depth,
   if (e != cudaSuccess) return cvd_fail("cvd_consistency_fwd_bwd: memset: %s", cudaGetErrorString(e));
   const int fg = f_dir_host != nullptr;
   const float f0 = fg ? f_dir_host[0] : 0.f, f1 = fg ? f_dir_host[1] : 0.f;
-  const bool vec = (W % 4 == 0) && ((((uintptr_t)depth | (uintptr_t)flow0 | (uintptr_t)flow1 | (uintptr_t)mask0 |
-                                      (uintptr_t)mask1 | (uintptr_t)grad_depth) & 15) == 0);
-  if (vec) {
-    const long long quads = HW / 4;
-    dim3 grid((unsigned)((quads + 255) / 256), B);
-    consistency_kernel<4><<<grid, 256, 0, st>>>(depth, flow0, flow1, mask0, mask1, extr, intr, msum,
-                                                 f0, f1, fg, lam_r, lam_b, B, B_global, H, W, acc, grad_depth);
-  } else {
-    dim3 grid((unsigned)((HW + 255) / 256), B);
-    consistency_kernel<1><<<grid, 256, 0, st>>>(depth, flow0, flow1, mask0, mask1, extr, intr, msum,
-                                                 f0, f1, fg, lam_r, lam_b, B, B_global, H, W, acc, grad_depth);
-  }
+  PairConst* consts = reinterpret_cast<PairConst*>(acc + 4 * (size_t)B);
+  consistency_setup<<<(2 * B + 127) / 128, 128, 0, st>>>(extr, intr, msum, f0, f1, fg, lam_r, lam_b, B, B_global, consts);
+  CVD_LAUNCH_OK("consistency_setup");
+  dim3 grid((unsigned)((HW + LOSS_THREADS * PIX - 1) / (LOSS_THREADS * PIX)), B);
+  const bool full = (HW % (LOSS_THREADS * PIX)) == 0;
+  const bool gr = grad_depth != nullptr, dr = lam_r > 0.f, dd = lam_b > 0.f;   // (:169,176)
+#define CVD_LOSS_LAUNCH(G, R, D, F)                                                                    \
+  consistency_kernel<G, R, D, F><<<grid, LOSS_THREADS, 0, st>>>(depth, flow0, flow1, mask0, mask1, consts, \
+      H, W, acc, grad_depth)
+#define CVD_LOSS_F(G, R, D) do { if (full) CVD_LOSS_LAUNCH(G, R, D, true); else CVD_LOSS_LAUNCH(G, R, D, false); } while (0)
+#define CVD_LOSS_D(G, R) do { if (dd) CVD_LOSS_F(G, R, true); else CVD_LOSS_F(G, R, false); } while (0)
+#define CVD_LOSS_R(G) do { if (dr) CVD_LOSS_D(G, true); else CVD_LOSS_D(G, false); } while (0)
+  if (gr) CVD_LOSS_R(true); else CVD_LOSS_R(false);
   CVD_LAUNCH_OK("consistency_kernel");
   consistency_finalize<<<1, 128, 0, st>>>(acc, msum, intr, f0, f1, fg, lam_r, lam_b, B, B_global, out_pair, out_loss);
   CVD_LAUNCH_OK("consistency_finalize");

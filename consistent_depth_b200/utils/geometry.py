@@ -24,7 +24,7 @@ class _Workspace:
         ws = cls._cache.get(key)
         if ws is None:
             ws = {
-                "acc": torch.empty(B * 4, dtype=torch.float64, device=dev),
+                "acc": torch.empty(int(_lib.lib().cvd_consistency_workspace_bytes(B)) // 8 + 2, dtype=torch.float64, device=dev),
                 "msum": torch.empty(B * 2, dtype=torch.float32, device=dev),
             }
             cls._cache[key] = ws

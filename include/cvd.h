@@ -56,7 +56,7 @@ long long   cvd_launch_count(void);
  *                          direction k (consistency_loss.py:178); NULL =>
  *                          computed on device from this call's intr.
  *   B_global               divisor of the final torch.mean over pairs (:208)
- *   acc        (B,2,2) f64 scratch, zeroed by the call
+ *   workspace  cvd_consistency_workspace_bytes(B) bytes of device scratch, 16-byte aligned
  *   out_pair   (2,B)  f32  [0]=lambda_r*reprojection[b], [1]=lambda_b*disparity[b]
  *                          (the reference's batch_losses dict)
  *   out_loss   (1)    f32  sum_b(out_pair)/B_global
@@ -64,6 +64,8 @@ long long   cvd_launch_count(void);
  */
 int cvd_mask_sums(const float* mask0, const float* mask1, int B, int H, int W,
                   float* msum, void* stream);
+
+size_t cvd_consistency_workspace_bytes(int B);
 
 int cvd_consistency_fwd_bwd(const float* depth,
                             const float* flow0, const float* flow1,
@@ -73,7 +75,7 @@ int cvd_consistency_fwd_bwd(const float* depth,
                             const float* f_dir_host,
                             float lambda_reprojection, float lambda_view_baseline,
                             int B, int B_global, int H, int W,
-                            double* acc, float* out_pair, float* out_loss,
+                            void* workspace, float* out_pair, float* out_loss,
                             float* grad_depth, void* stream);
 
 /* ---- fused Adam -----------------------------------------------------------
