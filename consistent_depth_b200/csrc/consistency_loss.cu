@@ -47,7 +47,7 @@ __device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.appro
 #define CVD_LOSS_PIX 4
 #endif
 #ifndef CVD_LOSS_MINB
-#define CVD_LOSS_MINB 3
+#define CVD_LOSS_MINB 4
 #endif
 constexpr int PIX = CVD_LOSS_PIX;   // pixels per thread, strided by the block size (lane <-> adjacent pixels)
 constexpr int LOSS_THREADS = 256;
