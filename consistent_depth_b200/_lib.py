@@ -20,12 +20,14 @@ class CvdError(RuntimeError):
 
 class cvd_src_t(C.Structure):
     _fields_ = [("x", C.c_void_p), ("dy", C.c_void_p), ("a", C.c_void_p), ("b", C.c_void_p),
-                ("bw", C.c_void_p), ("c_total", C.c_int), ("c_off", C.c_int),
-                ("dy_ctotal", C.c_int), ("dy_coff", C.c_int), ("relu", C.c_int), ("mode", C.c_int)]
+                ("bw", C.c_void_p),
+                ("c_total", C.c_int), ("c_off", C.c_int), ("n0", C.c_int), ("gap", C.c_int),
+                ("dy_ctotal", C.c_int), ("dy_coff", C.c_int), ("dy_n0", C.c_int), ("dy_gap", C.c_int),
+                ("relu", C.c_int), ("mode", C.c_int)]
 
 
 class cvd_dst_t(C.Structure):
-    _fields_ = [("y", C.c_void_p), ("c_total", C.c_int), ("c_off", C.c_int), ("ncols", C.c_int)]
+    _fields_ = [("y", C.c_void_p), ("c_total", C.c_int), ("c_off", C.c_int), ("n0", C.c_int), ("gap", C.c_int)]
 
 
 _lib = None
@@ -43,6 +45,7 @@ def lib():
         _lib.cvd_last_error.restype = C.c_char_p
         _lib.cvd_launch_count.restype = C.c_longlong
         _lib.cvd_consistency_workspace_bytes.restype = C.c_size_t
+        _lib.cvd_conv_packed_bytes.restype = C.c_size_t
     return _lib
 
 

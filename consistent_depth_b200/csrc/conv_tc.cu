@@ -1,0 +1,427 @@
+// tcgen05 implicit-GEMM convolution (forward and input-gradient) for the depth CNNs.
+//
+// Replaces nn.Conv2d forward (monodepth/mannequin_challenge/models/hourglass.py:27,39,42,164,173)
+// and the dgrad half of its autograd backward (depth_fine_tuning.py:282), with the
+// BatchNorm2d(train)+ReLU that PRECEDES the conv (hourglass.py:28-29,40-41,43-44,165-166) applied
+// while the activation tile is staged ("normalise on load"), and for dgrad the BatchNorm+ReLU
+// BACKWARD of the conv's output applied the same way.
+//
+// Formulation (stride 1, "same" zero padding):   D[pixel, co] = sum_{tap, ci} A_tap[pixel, ci] * W[co, tap, ci]
+//   M = 128 output pixels  (an 8-wide x 16-tall patch: 16 groups of 8 x-adjacent pixels)
+//   N = Cout (16..256)     K = taps x Cin, walked in k-blocks of 16 channels of one tap
+// HBM layout: NHWC fp32 activations, each conv reads/writes a channel VIEW (offset, gap) of a wider buffer
+//   so torch.cat is free.
+// SMEM layout of the activation halo tile (the key to the design): bf16, channel-chunk-major
+//   [chunk of 8 channels][halo row][halo col][8 ch = 16 B]
+// which is exactly the UMMA SWIZZLE_NONE K-major canonical layout: 8 x-adjacent pixels x 16 B form one
+// contiguous 128-B core matrix; the next 8-pixel group (next patch row) is SBO = halo_row_pitch away, the
+// next 8 channels are LBO = plane_stride away.  A filter tap (ky,kx) is then JUST A DIFFERENT START
+// ADDRESS of the A descriptor: the halo tile is staged once and re-used by all k*k taps from shared
+// memory; im2col never exists, and HBM/L2 sees each input element ~once per CTA.
+// Precision: bf16 tensor cores with the operands split v = hi + lo (3 MMAs: hi*hi, lo*hi, hi*lo,
+// fp32 accumulate in TMEM) => fp32-class results ("precision 3"), or plain bf16 ("precision 1").
+//
+// Warp roles (192 threads): warp 0 = TMEM allocator + single-thread MMA issuer; warp 1 = weight
+// streamer (cp.async.bulk of pre-packed core-matrix blobs through an mbarrier ring); warps 2-5 =
+// activation producers (global -> transform -> bf16 hi/lo -> smem), then epilogue
+// (tcgen05.ld -> +bias / exp -> NHWC global stores).
+#include "cvd_common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kProducerThreads = 128;
+constexpr int kMaxStages = 8;
+constexpr int kGroupCh = 64;          // channels per activation group resident in one A slot
+
+struct ConvArgs {
+  // source view
+  const float* x; const float* dy; const float* a; const float* b; const float4* bw;
+  int x_ct, x_c0, x_n0, x_gap;
+  int dy_ct, dy_c0, dy_n0, dy_gap;
+  int relu, mode, cin_valid;
+  // weights / bias
+  const uint8_t* wp; const float* bias;
+  // destination view
+  float* y; int y_ct, y_c0, y_n0, y_gap; int cout_valid;
+  // problem
+  int N, H, W, cin, cout, k, pad;
+  int flags, nsplit;                 // nsplit: 1 (bf16) or 3 (bf16x3)
+  // tiling
+  int mtx, mty, tiles_x, tiles_y;    // M-tiles per CTA along x / y
+  int HP, WP, plane_bytes;           // halo dims, bytes of one 8-channel plane (padded)
+  int slot_bytes, nslots, ngroups, gchunks;   // chunks (8 ch) per group
+  int stage_bytes, nstages;
+  int tmem_cols;
+};
+
+__device__ __forceinline__ int view_phys(int c, int c0, int n0, int gap) { return c0 + c + (c >= n0 ? gap : 0); }
+
+// ------------------------------------------------------------------ activation producer
+// Fills one A slot with channel group `g` of the halo tile whose top-left output pixel is (oy, ox).
+__device__ __forceinline__ void fill_slot(const ConvArgs& p, uint8_t* slot, int g, int n, int oy, int ox, int tid)
+{
+  const int gch = min(p.gchunks, (p.cin - g * kGroupCh) >> 3);   // 8-channel chunks in this group
+  const int npix = p.HP * p.WP;
+  const int total = npix * gch;
+  const int lo_off = p.gchunks * p.plane_bytes;        // lo planes follow the (max-sized) hi plane set
+  const size_t img_off = (size_t)n * p.H * p.W;
+  for (int it = tid; it < total; it += kProducerThreads) {
+    const int c8 = it % gch;                           // chunk fastest: consecutive threads read consecutive 32 B
+    const int hp = it / gch;
+    const int hy = hp / p.WP, hx = hp - hy * p.WP;
+    const int iy = oy + hy - p.pad, ix = ox + hx - p.pad;
+    const int cl = g * kGroupCh + c8 * 8;              // logical first channel of the chunk
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W && cl < p.cin_valid) {
+      const size_t pix = img_off + (size_t)iy * p.W + ix;
+      const int pc = view_phys(cl, p.x_c0, p.x_n0, p.x_gap);
+      const float* xp = p.x + pix * p.x_ct + pc;
+      const bool second = cl + 4 < p.cin_valid;
+      float4 x0 = __ldg(reinterpret_cast<const float4*>(xp));
+      float4 x1 = second ? __ldg(reinterpret_cast<const float4*>(xp + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      if (p.a) {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 a0 = __ldg(reinterpret_cast<const float4*>(p.a + pc)), a1 = second ? __ldg(reinterpret_cast<const float4*>(p.a + pc + 4)) : z4;
+        float4 b0 = __ldg(reinterpret_cast<const float4*>(p.b + pc)), b1 = second ? __ldg(reinterpret_cast<const float4*>(p.b + pc + 4)) : z4;
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xv[i] = fmaf(av[i], xv[i], bv[i]);
+      }
+      if (p.mode == CVD_XF_AFFINE) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = p.relu ? fmaxf(xv[i], 0.f) : xv[i];
+      } else {
+        // BatchNorm(+ReLU) backward on load: y = a x + b ; g = dy * [y > 0] ; dx = c0 g - c1 - c2 y
+        const int dc = view_phys(cl, p.dy_c0, p.dy_n0, p.dy_gap);
+        const float* dp = p.dy + pix * p.dy_ct + dc;
+        float4 d0 = __ldg(reinterpret_cast<const float4*>(dp));
+        float4 d1 = second ? __ldg(reinterpret_cast<const float4*>(dp + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i >= 4 && !second) break;
+          const float4 c = __ldg(p.bw + pc + i);
+          const float gq = (!p.relu || xv[i] > 0.f) ? dv[i] : 0.f;
+          v[i] = c.x * gq - c.y - c.z * xv[i];
+        }
+      }
+      if (!second) {
+#pragma unroll
+        for (int i = 4; i < 8; ++i) v[i] = 0.f;
+      }
+    }
+    uint4 hi, lo;
+    tc::split8(v, hi, lo);
+    uint8_t* dst = slot + (size_t)c8 * p.plane_bytes + (size_t)hp * 16;
+    *reinterpret_cast<uint4*>(dst) = hi;
+    if (p.nsplit == 3) *reinterpret_cast<uint4*>(dst + lo_off) = lo;
+  }
+}
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const ConvArgs p)
+{
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // layout: [A slots][B stages][barriers]
+  uint8_t* a_slots = smem;
+  uint8_t* b_stages = a_slots + (size_t)p.nslots * p.slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_stages + (size_t)p.nstages * p.stage_bytes);
+  uint64_t* b_full = bars;                       // [kMaxStages]
+  uint64_t* b_empty = bars + kMaxStages;         // [kMaxStages]
+  uint64_t* a_full = bars + 2 * kMaxStages;      // [2]
+  uint64_t* a_empty = a_full + 2;                // [2]
+  uint64_t* acc_full = a_empty + 2;              // [1]
+  uint32_t* tmem_base_sh = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tx = t % p.tiles_x; t /= p.tiles_x;
+  const int ty = t % p.tiles_y; const int n = t / p.tiles_y;
+  const int ox = tx * (8 * p.mtx), oy = ty * (16 * p.mty);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.nstages; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&a_full[i], kProducerThreads); tc::mbar_init(&a_empty[i], 1); }
+    tc::mbar_init(acc_full, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 0) {
+    tc::tmem_alloc_dyn(tmem_base_sh, (uint32_t)p.tmem_cols);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_sh;
+
+  const int taps = p.k * p.k;
+  const int MT = p.mtx * p.mty;
+  const int kb_total = taps * (p.cin >> 4);                      // number of weight stages streamed
+
+  if (warp == 0) {
+    // ============================ MMA issuer (one thread) ============================
+    if (lane == 0) {
+      const uint32_t idesc = tc::idesc_bf16(128, p.cout, 0, 0);
+      const uint32_t a_base = tc::smem_u32(a_slots), b_base = tc::smem_u32(b_stages);
+      const uint32_t lo_a = (uint32_t)p.gchunks * p.plane_bytes;      // hi -> lo plane offset inside a slot
+      const uint32_t lo_b = (uint32_t)p.cout * 32;                     // hi -> lo blob offset inside a stage
+      const uint32_t sbo_a = (uint32_t)p.WP * 16;
+      int stage = 0; uint32_t bphase = 0;
+      for (int g = 0; g < p.ngroups; ++g) {
+        const int slot = g % p.nslots;
+        tc::mbar_wait(&a_full[slot], (uint32_t)((g / p.nslots) & 1));
+        tc::tc_fence_after();
+        const uint32_t slot_addr = a_base + (uint32_t)slot * p.slot_bytes;
+        const int kbg = min(kGroupCh, p.cin - g * kGroupCh) >> 4;      // 16-channel k-blocks in this group
+        for (int tap = 0; tap < taps; ++tap) {
+          const int ky = tap / p.k, kx = tap - ky * p.k;
+          for (int kb = 0; kb < kbg; ++kb) {
+            tc::mbar_wait(&b_full[stage], bphase);
+            tc::tc_fence_after();
+            const uint32_t bs = b_base + (uint32_t)stage * p.stage_bytes;
+            const uint64_t bd_hi = tc::smem_desc(bs, 128, 256);
+            const uint64_t bd_lo = tc::smem_desc(bs + lo_b, 128, 256);
+            const bool first_k = (g == 0 && tap == 0 && kb == 0);
+            for (int my = 0; my < p.mty; ++my) {
+              for (int mx = 0; mx < p.mtx; ++mx) {
+                const uint32_t a_addr = slot_addr + (uint32_t)(2 * kb) * p.plane_bytes +
+                                        (uint32_t)(((my * 16 + ky) * p.WP) + kx + mx * 8) * 16;
+                const uint32_t d = tmem_base + (uint32_t)((my * p.mtx + mx) * p.cout);
+                const uint64_t ad_hi = tc::smem_desc(a_addr, (uint32_t)p.plane_bytes, sbo_a);
+                tc::umma_f16(d, ad_hi, bd_hi, idesc, first_k ? 0u : 1u);
+                if (p.nsplit == 3) {
+                  const uint64_t ad_lo = tc::smem_desc(a_addr + lo_a, (uint32_t)p.plane_bytes, sbo_a);
+                  tc::umma_f16(d, ad_lo, bd_hi, idesc, 1u);
+                  tc::umma_f16(d, ad_hi, bd_lo, idesc, 1u);
+                }
+              }
+            }
+            tc::umma_commit(&b_empty[stage]);        // weight stage reusable once these MMAs retire
+            if (++stage == p.nstages) { stage = 0; bphase ^= 1; }
+          }
+        }
+        tc::umma_commit(&a_empty[slot]);             // activation slot reusable
+      }
+      tc::umma_commit(acc_full);                     // accumulators complete
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================ weight streamer ============================
+    if (lane == 0) {
+      int stage = 0; uint32_t ephase = 0;
+      const uint8_t* src = p.wp;
+      for (int i = 0; i < kb_total; ++i) {
+        if (i >= p.nstages) tc::mbar_wait(&b_empty[stage], ephase);
+        tc::mbar_arrive_expect_tx(&b_full[stage], (uint32_t)p.stage_bytes);
+        tc::bulk_g2s(b_stages + (size_t)stage * p.stage_bytes, src, (uint32_t)p.stage_bytes, &b_full[stage]);
+        src += p.stage_bytes;
+        if (++stage == p.nstages) { stage = 0; if (i >= p.nstages) ephase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================ activation producers, then epilogue ============================
+    const int tid = threadIdx.x - 64;
+    for (int g = 0; g < p.ngroups; ++g) {
+      const int slot = g % p.nslots;
+      if (g >= p.nslots) tc::mbar_wait(&a_empty[slot], (uint32_t)(((g / p.nslots) - 1) & 1));
+      fill_slot(p, a_slots + (size_t)slot * p.slot_bytes, g, n, oy, ox, tid);
+      tc::fence_proxy_async_smem();
+      tc::mbar_arrive(&a_full[slot]);
+    }
+
+    tc::mbar_wait(acc_full, 0);
+    tc::tc_fence_after();
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;                   // accumulator row = pixel inside the M-tile
+    const int py = row >> 3, px = row & 7;
+    const bool accum = (p.flags & 1) != 0, do_exp = (p.flags & 2) != 0;
+    for (int my = 0; my < p.mty; ++my) {
+      for (int mx = 0; mx < p.mtx; ++mx) {
+        const int yy = oy + my * 16 + py, xx = ox + mx * 8 + px;
+        const bool inside = yy < p.H && xx < p.W;
+        float* yp = p.y + (((size_t)n * p.H + (inside ? yy : 0)) * p.W + (inside ? xx : 0)) * p.y_ct;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((my * p.mtx + mx) * p.cout);
+        for (int c16 = 0; c16 < p.cout; c16 += 16) {
+          float v[16];
+          tc::tmem_ld16(taddr + (uint32_t)c16, v);    // warp-collective: executed by all lanes
+          if (!inside || c16 >= p.cout_valid) continue;
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (c16 + i < p.cout_valid) v[i] += __ldg(p.bias + c16 + i);
+          }
+          if (do_exp) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = expf(v[i]);
+          }
+          float* dst = yp + view_phys(c16, p.y_c0, p.y_n0, p.y_gap);
+          if (c16 + 16 <= p.cout_valid) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              if (accum) { const float4 old = *reinterpret_cast<const float4*>(dst + i); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+              *reinterpret_cast<float4*>(dst + i) = o;
+            }
+          } else {
+            for (int i = 0; i < p.cout_valid - c16; ++i) dst[i] = accum ? dst[i] + v[i] : v[i];
+          }
+        }
+      }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------ weight packing
+// fp32 OIHW -> per (group, tap, k-block) blobs [hi: cout x 16 ch][lo: cout x 16 ch], each in the
+// UMMA SWIZZLE_NONE K-major core-matrix order: blob[n/8][kk/8][n%8][kk%8] (LBO = 128 B, SBO = 256 B).
+// transpose_flip builds the dgrad operand: W'[ci][co][k-1-ky][k-1-kx].
+__global__ void pack_weights_kernel(const float* __restrict__ w, int cin_w, int cout_w, int k, int transpose_flip,
+                                    int cin_pad, int cout_pad, int nsplit, uint8_t* __restrict__ out)
+{
+  // logical GEMM dims: K-channels = cin_pad (multiple of 16), N = cout_pad (multiple of 16)
+  const int taps = k * k;
+  const int ngroups = (cin_pad + kGroupCh - 1) / kGroupCh;
+  const int stage_bytes = cout_pad * 32 * (nsplit == 3 ? 2 : 1);
+  const long long total = (long long)cin_pad * cout_pad * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cin_pad);
+    const int nn = (int)((i / cin_pad) % cout_pad);
+    const int tap = (int)(i / ((long long)cin_pad * cout_pad));
+    const int ky = tap / k, kx = tap - ky * k;
+    float v = 0.f;
+    if (!transpose_flip) {
+      if (c < cin_w && nn < cout_w) v = w[(((size_t)nn * cin_w + c) * k + ky) * k + kx];
+    } else {
+      // GEMM "cin" = forward Cout (w dim 0), GEMM "cout" = forward Cin (w dim 1)
+      if (c < cout_w && nn < cin_w) v = w[(((size_t)c * cin_w + nn) * k + (k - 1 - ky)) * k + (k - 1 - kx)];
+    }
+    const int g = c / kGroupCh, cg = c - g * kGroupCh;
+    const int gch = min(kGroupCh, cin_pad - g * kGroupCh);
+    const int kbg = gch / 16;
+    // stage index: groups before g contribute taps * (their kb count) stages
+    const int stage = g * taps * (kGroupCh / 16) + tap * kbg + cg / 16;
+    const int kk = cg & 15;
+    const size_t off = (size_t)stage * stage_bytes + (size_t)(nn >> 3) * 256 + (size_t)(kk >> 3) * 128 + (size_t)(nn & 7) * 16 + (size_t)(kk & 7) * 2;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    *reinterpret_cast<__nv_bfloat16*>(out + off) = h;
+    if (nsplit == 3) *reinterpret_cast<__nv_bfloat16*>(out + off + (size_t)cout_pad * 32) = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+extern "C" size_t cvd_conv_packed_bytes(int cin, int cout, int k, int precision)
+{
+  const int cin_pad = round_up(cin, 16), cout_pad = round_up(cout, 16);
+  return (size_t)cin_pad * cout_pad * k * k * 2 * (precision == 3 ? 2 : 1);
+}
+
+extern "C" int cvd_conv_pack_weights(const float* w_oihw, int cin, int cout, int k, int transpose_flip,
+                                     int precision, void* packed, void* stream)
+{
+  CVD_CHECK_ARG(w_oihw && packed, "cvd_conv_pack_weights: null pointer");
+  CVD_CHECK_ARG(precision == 1 || precision == 3, "cvd_conv_pack_weights: precision must be 1 or 3");
+  // forward: GEMM K-channels = cin, N = cout; dgrad: K-channels = cout, N = cin
+  const int kc = transpose_flip ? cout : cin, nc = transpose_flip ? cin : cout;
+  const int cin_pad = round_up(kc, 16), cout_pad = round_up(nc, 16);
+  const long long total = (long long)cin_pad * cout_pad * k * k;
+  long long blocks = (total + 255) / 256; if (blocks > 4096) blocks = 4096;
+  pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, cin, cout, k, transpose_flip,
+                                                                          cin_pad, cout_pad, precision, (uint8_t*)packed);
+  CVD_LAUNCH_OK("pack_weights_kernel");
+  return 0;
+}
+
+extern "C" int cvd_conv_fwd(const cvd_src_t* src, const void* packed_w, const float* bias,
+                            const cvd_dst_t* dst, int N, int H, int W, int cin, int cout, int k,
+                            int precision, int flags, void* stream)
+{
+  CVD_CHECK_ARG(src && dst && packed_w && src->x && dst->y, "cvd_conv_fwd: null pointer");
+  CVD_CHECK_ARG(precision == 1 || precision == 3, "cvd_conv_fwd: precision must be 1 (bf16) or 3 (bf16x3)");
+  CVD_CHECK_ARG(k >= 1 && k <= 11 && (k & 1), "cvd_conv_fwd: k=%d unsupported (odd, <= 11)", k);
+  CVD_CHECK_ARG(N > 0 && H > 0 && W > 0, "cvd_conv_fwd: bad shape");
+  CVD_CHECK_ARG(src->mode == CVD_XF_AFFINE || (src->mode == CVD_XF_BNBWD && src->dy && src->bw && src->a && src->b),
+                "cvd_conv_fwd: bad source transform");
+  CVD_CHECK_ARG((src->c_total & 3) == 0 && (src->c_off & 3) == 0 && (src->n0 & 7) == 0 && (src->gap & 3) == 0,
+                "cvd_conv_fwd: source view must be 4-channel aligned");
+  CVD_CHECK_ARG((dst->c_total & 3) == 0 || dst->c_total == 1, "cvd_conv_fwd: destination channel stride must be a multiple of 4 (or 1)");
+  ConvArgs p{};
+  p.x = src->x; p.dy = src->dy; p.a = src->a; p.b = src->b; p.bw = reinterpret_cast<const float4*>(src->bw);
+  p.x_ct = src->c_total; p.x_c0 = src->c_off; p.x_n0 = src->n0 > 0 ? src->n0 : (1 << 30); p.x_gap = src->gap;
+  p.dy_ct = src->dy_ctotal; p.dy_c0 = src->dy_coff; p.dy_n0 = src->dy_n0 > 0 ? src->dy_n0 : (1 << 30); p.dy_gap = src->dy_gap;
+  p.relu = src->relu; p.mode = src->mode;
+  p.cin_valid = round_up(cin, 4);
+  p.wp = (const uint8_t*)packed_w; p.bias = bias;
+  p.y = dst->y; p.y_ct = dst->c_total; p.y_c0 = dst->c_off; p.y_n0 = dst->n0 > 0 ? dst->n0 : (1 << 30); p.y_gap = dst->gap;
+  p.cout_valid = cout;
+  p.N = N; p.H = H; p.W = W; p.k = k; p.pad = (k - 1) / 2;
+  p.cin = round_up(cin, 16); p.cout = round_up(cout, 16);
+  CVD_CHECK_ARG(p.cout <= 256, "cvd_conv_fwd: cout=%d > 256", cout);
+  p.flags = flags; p.nsplit = precision;
+  p.ngroups = (p.cin + kGroupCh - 1) / kGroupCh;
+  p.gchunks = (p.ngroups == 1 ? p.cin : kGroupCh) / 8;
+  p.stage_bytes = p.cout * 32 * (precision == 3 ? 2 : 1);
+
+  // choose the CTA tile: as many 8x16 M-tiles as TMEM (512 cols) and shared memory allow
+  const int smem_budget = 200 * 1024;
+  int best_mtx = 0, best_mty = 0, best_nslots = 1, best_nst = 2;
+  const int cand[6][2] = {{4, 2}, {4, 1}, {2, 2}, {2, 1}, {1, 2}, {1, 1}};   // (mtx, mty), largest first
+  for (int ci = 0; ci < 6 && !best_mtx; ++ci) {
+    const int mtx = cand[ci][0], mty = cand[ci][1];
+    if (mtx * mty * p.cout > 512) continue;
+    if (8 * mtx > round_up(W, 8) && mtx > 1) continue;
+    if (16 * mty > round_up(H, 16) && mty > 1) continue;
+    const int HP = 16 * mty + k - 1, WP = 8 * mtx + k - 1;
+    int plane = HP * WP * 16;
+    // producer store bank spreading: plane stride = 16*q (mod 128) with q = pixels per quarter-warp
+    const int q = p.gchunks >= 8 ? 1 : 8 / p.gchunks;
+    plane = (plane + 127) / 128 * 128 + 16 * q;
+    const int slot = plane * p.gchunks * (precision == 3 ? 2 : 1);
+    const int nslots = p.ngroups > 1 ? 2 : 1;
+    for (int nst = kMaxStages; nst >= 2; --nst) {
+      if ((size_t)nslots * slot + (size_t)nst * p.stage_bytes + 1024 <= (size_t)smem_budget) {
+        best_mtx = mtx; best_mty = mty; best_nslots = nslots; best_nst = nst;
+        p.HP = HP; p.WP = WP; p.plane_bytes = plane; p.slot_bytes = slot;
+        break;
+      }
+    }
+  }
+  CVD_CHECK_ARG(best_mtx > 0, "cvd_conv_fwd: no tile fits shared memory (cin=%d cout=%d k=%d)", cin, cout, k);
+  p.mtx = best_mtx; p.mty = best_mty; p.nslots = best_nslots; p.nstages = best_nst;
+  const int kb_total = k * k * (p.cin >> 4);
+  if (p.nstages > kb_total) p.nstages = kb_total < 1 ? 1 : kb_total;
+  p.tiles_x = (W + 8 * p.mtx - 1) / (8 * p.mtx);
+  p.tiles_y = (H + 16 * p.mty - 1) / (16 * p.mty);
+  int cols = p.mtx * p.mty * p.cout, pw = 32;
+  while (pw < cols) pw <<= 1;
+  p.tmem_cols = pw;
+  CVD_CHECK_ARG(p.plane_bytes < (1 << 18) && p.WP * 16 < (1 << 18), "cvd_conv_fwd: descriptor offset overflow");
+
+  const size_t smem = (size_t)p.nslots * p.slot_bytes + (size_t)p.nstages * p.stage_bytes + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) return cvd_fail("cvd_conv_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = 227 * 1024;
+  }
+  const long long grid = (long long)N * p.tiles_x * p.tiles_y;
+  CVD_CHECK_ARG(grid < (1ll << 31), "cvd_conv_fwd: grid too large");
+  conv_tc_kernel<<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+  CVD_LAUNCH_OK("conv_tc_kernel");
+  return 0;
+}

@@ -97,6 +97,60 @@ int cvd_adam_flat(float* p, const float* g, float* m, float* v, long long n,
 int cvd_param_l1(const float* p, const float* p0, long long n, float lambda,
                  float* g_accum, float* out_loss_accum, void* stream);
 
+/* ---- conv engine (tcgen05 implicit GEMM), csrc/conv_tc.cu ------------------
+ * Activations are NHWC fp32.  A conv reads / writes a channel VIEW of a wider
+ * buffer: logical channel c lives at physical channel
+ *      c_off + c + (c >= n0 ? gap : 0)          (n0 <= 0: no gap)
+ * so torch.cat (hourglass.py:55) costs nothing.
+ *
+ * Per-channel input transform applied while the activation tile is staged:
+ *   CVD_XF_AFFINE : v = a[c]*x + b[c] (a == NULL: identity); if relu: v = max(v,0)
+ *                   == BatchNorm2d(train) + ReLU of the PRODUCER layer (hourglass.py:28-29)
+ *   CVD_XF_BNBWD  : y = a[c]*x + b[c]; g = (!relu || y > 0) ? dy : 0;
+ *                   v = bw[c].x*g - bw[c].y - bw[c].z*y
+ *                   == backward of that BatchNorm+ReLU (autograd, depth_fine_tuning.py:282)
+ * a / b / bw are indexed by PHYSICAL channel of x.
+ */
+#define CVD_XF_AFFINE 0
+#define CVD_XF_BNBWD  1
+
+typedef struct {
+  const float* x;        /* NHWC fp32 tensor, c_total channels per pixel            */
+  const float* dy;       /* BNBWD only: gradient wrt the post-activation tensor     */
+  const float* a;        /* per-channel scale or NULL                               */
+  const float* b;        /* per-channel shift or NULL                               */
+  const float* bw;       /* BNBWD only: [C][4] floats (c0, c1, c2, unused)          */
+  int c_total, c_off, n0, gap;
+  int dy_ctotal, dy_coff, dy_n0, dy_gap;
+  int relu;
+  int mode;              /* CVD_XF_*                                                */
+} cvd_src_t;
+
+typedef struct {
+  float* y;              /* NHWC fp32 destination                                   */
+  int c_total, c_off, n0, gap;
+} cvd_dst_t;
+
+/* Packs fp32 OIHW conv weights (torch layout, hourglass.py:27,39,42) into bf16
+ * hi(/lo) UMMA core-matrix blobs, one per (tap, 16-channel k-block), that the
+ * conv kernel streams with cp.async.bulk.  transpose_flip != 0 builds the dgrad
+ * operand (Cin<->Cout swapped, taps rotated 180 degrees).
+ * precision: 1 = bf16, 3 = bf16x3 split (hi+lo, fp32-class). */
+size_t cvd_conv_packed_bytes(int cin, int cout, int k, int precision);
+int cvd_conv_pack_weights(const float* w_oihw, int cin, int cout, int k, int transpose_flip,
+                          int precision, void* packed, void* stream);
+
+/* Convolution, stride 1, "same" zero padding, over N images of HxW: replaces
+ * nn.Conv2d forward (hourglass.py:27,39,42,164,173).  With transpose_flip
+ * weights (cin/cout given in GEMM terms: cin = channels of the tensor being
+ * read) and a CVD_XF_BNBWD source it is the conv input-gradient.
+ *   flags bit0: accumulate into dst (+=) ; bit1: exp() epilogue
+ *         (mannequin_challenge_model.py:66)
+ */
+int cvd_conv_fwd(const cvd_src_t* src, const void* packed_w, const float* bias,
+                 const cvd_dst_t* dst, int N, int H, int W, int cin, int cout, int k,
+                 int precision, int flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
