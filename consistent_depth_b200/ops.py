@@ -40,6 +40,7 @@ def make_src(x, a=None, b=None, relu=False, dy=None, bw=None):
         s.bw = bw.data_ptr()
     else:
         s.mode = XF_AFFINE
+    s._keep = (x.t, a, b, dy.t if dy is not None else None, bw)   # keep the tensors alive with the struct
     return s
 
 
@@ -47,6 +48,7 @@ def make_dst(y):
     d = cvd_dst_t()
     d.y = y.t.data_ptr()
     d.c_total, d.c_off, d.n0, d.gap = y.c_total, y.off, y.n0, y.gap
+    d._keep = (y.t,)
     return d
 
 
@@ -69,3 +71,64 @@ def conv(src, packed, bias, dst, N, H, W, cin, cout, k, precision=3, flags=0):
     """src: cvd_src_t, dst: cvd_dst_t (from make_src/make_dst); cin/cout in GEMM terms."""
     _lib.check(_lib.lib().cvd_conv_fwd(C.byref(src), _lib.ptr(packed), _lib.ptr(bias), C.byref(dst),
                                        N, H, W, cin, cout, k, precision, flags, _lib.stream()), "cvd_conv_fwd")
+
+
+def conv_wgrad(gsrc, xsrc, dw, N, H, W, cin, cout, k, precision=3):
+    """dw (fp32 OIHW, pre-zeroed or accumulating) += G (x) X."""
+    _lib.check(_lib.lib().cvd_conv_wgrad(C.byref(gsrc), C.byref(xsrc), _lib.ptr(dw), N, H, W, cin, cout, k,
+                                         precision, _lib.stream()), "cvd_conv_wgrad")
+
+
+def bn_scratch(device, C=256):
+    n = int(_lib.lib().cvd_bn_scratch_bytes(C))
+    return torch.zeros((n + 7) // 8, dtype=torch.float64, device=device)
+
+
+def bn_stats(x, c_off, Cn, npix, scratch, a, b, rstd, mean, gamma=None, beta=None, running_mean=None,
+             running_var=None, eps=1e-5, momentum=0.1):
+    _lib.check(_lib.lib().cvd_bn_stats(_lib.ptr(x), x.shape[-1], c_off, Cn, C.c_longlong(npix), _lib.ptr(scratch),
+                                       _lib.ptr(gamma), _lib.ptr(beta), C.c_float(eps), C.c_float(momentum),
+                                       _lib.ptr(running_mean), _lib.ptr(running_var), _lib.ptr(a), _lib.ptr(b),
+                                       _lib.ptr(rstd), _lib.ptr(mean), _lib.stream()), "cvd_bn_stats")
+
+
+def bn_bwd_reduce(x, c_off, Cn, dy, npix, scratch, a, b, rstd, mean, bw, relu=True, gamma=None, beta=None,
+                  dgamma=None, dbeta=None, dbias=None, dy_view=None):
+    """dy defaults to the same physical layout as x (dy_view = (c_total, c_off, n0, gap, lc0) overrides)."""
+    if dy_view is None:
+        dy_view = (dy.shape[-1], 0, 0, 0, c_off)
+    _lib.check(_lib.lib().cvd_bn_bwd_reduce(_lib.ptr(x), x.shape[-1], c_off, _lib.ptr(dy), dy_view[0], dy_view[1],
+                                            dy_view[2], dy_view[3], dy_view[4], _lib.ptr(a), _lib.ptr(b),
+                                            _lib.ptr(rstd), _lib.ptr(mean), _lib.ptr(gamma), _lib.ptr(beta),
+                                            1 if relu else 0, C.c_longlong(npix), Cn, _lib.ptr(scratch), _lib.ptr(bw),
+                                            _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.ptr(dbias), _lib.stream()),
+               "cvd_bn_bwd_reduce")
+
+
+def pool_fwd(xv, a, b, relu, p, N, H, W, Cn):
+    _lib.check(_lib.lib().cvd_pool_fwd(_lib.ptr(xv.t), xv.c_total, xv.off, xv.n0, xv.gap, _lib.ptr(a), _lib.ptr(b),
+                                       1 if relu else 0, _lib.ptr(p), N, H, W, Cn, _lib.stream()), "cvd_pool_fwd")
+
+
+def pool_bwd(dp, dx, accumulate, N, H, W, Cn):
+    _lib.check(_lib.lib().cvd_pool_bwd(_lib.ptr(dp), _lib.ptr(dx), 1 if accumulate else 0, N, H, W, Cn,
+                                       _lib.stream()), "cvd_pool_bwd")
+
+
+def merge_up_fwd(x1v, a1, b1, x2v, a2, b2, z, N, H, W, Cn):
+    _lib.check(_lib.lib().cvd_merge_up_fwd(_lib.ptr(x1v.t), x1v.c_total, x1v.off, x1v.n0, x1v.gap, _lib.ptr(a1), _lib.ptr(b1),
+                                           _lib.ptr(x2v.t), x2v.c_total, x2v.off, x2v.n0, x2v.gap, _lib.ptr(a2), _lib.ptr(b2),
+                                           _lib.ptr(z), N, H, W, Cn, _lib.stream()), "cvd_merge_up_fwd")
+
+
+def up2x_bwd(dz, dy2, N, H, W, Cn):
+    _lib.check(_lib.lib().cvd_up2x_bwd(_lib.ptr(dz), _lib.ptr(dy2), N, H, W, Cn, _lib.stream()), "cvd_up2x_bwd")
+
+
+def image_to_nhwc4(img, out, N, H, W):
+    _lib.check(_lib.lib().cvd_image_to_nhwc4(_lib.ptr(img), _lib.ptr(out), N, H, W, _lib.stream()), "cvd_image_to_nhwc4")
+
+
+def dlogdepth(grad_depth, depth, out4, dbias=None):
+    _lib.check(_lib.lib().cvd_dlogdepth(_lib.ptr(grad_depth), _lib.ptr(depth), _lib.ptr(out4),
+                                        C.c_longlong(depth.numel()), _lib.ptr(dbias), _lib.stream()), "cvd_dlogdepth")

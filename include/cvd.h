@@ -151,6 +151,60 @@ int cvd_conv_fwd(const cvd_src_t* src, const void* packed_w, const float* bias,
                  const cvd_dst_t* dst, int N, int H, int W, int cin, int cout, int k,
                  int precision, int flags, void* stream);
 
+/* Weight gradient of the same convolution: dW (fp32 OIHW, [cout][cin][k][k]) += sum over all
+ * pixels of G (x) X, the wgrad half of autograd's conv backward (depth_fine_tuning.py:282).
+ * gsrc: view of the gradient wrt the conv's raw output (CVD_XF_BNBWD of the following BatchNorm,
+ * or CVD_XF_AFFINE for a plain gradient tensor); xsrc: the conv's input as the forward saw it.
+ * Partial sums are RED-accumulated: the caller zeroes dW first. */
+int cvd_conv_wgrad(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oihw,
+                   int N, int H, int W, int cin, int cout, int k, int precision, void* stream);
+
+/* ---- BatchNorm bookkeeping / elementwise glue (csrc/elementwise.cu) -------
+ * nn.BatchNorm2d in TRAIN mode (hourglass.py:28,40,43,165): batch statistics of the raw conv
+ * output x (physical channels [c_off, c_off+C) of a c_total-wide NHWC buffer) over npix pixels ->
+ *   a[c_off+c] = gamma*rstd, b[c_off+c] = beta - mean*a   (consumed by CVD_XF_AFFINE on load)
+ *   rstd / mean saved for backward; running_mean/var updated (momentum, unbiased var).
+ * gamma/beta/running_* are the layer's own [C] arrays (NULL: affine=False / no running stats).
+ * scratch: cvd_bn_scratch_bytes(C) bytes, zeroed once by the caller, self-cleaning afterwards. */
+size_t cvd_bn_scratch_bytes(int C);
+int cvd_bn_stats(const float* x, int c_total, int c_off, int C, long long npix, void* scratch,
+                 const float* gamma, const float* beta, float eps, float momentum,
+                 float* running_mean, float* running_var,
+                 float* a, float* b, float* rstd, float* mean, void* stream);
+
+/* BatchNorm(+ReLU) backward reductions for the same channel range: with y = a x + b,
+ * g = dy*[y>0 or !relu]:  bw[c_off+c] = (c0, c1, c2, 0) such that d x = c0 g - c1 - c2 y
+ * (what CVD_XF_BNBWD applies on load), plus dgamma/dbeta (affine BN) and the gradient of the
+ * conv bias feeding this BN (dbias = sum d x), each [C] or NULL.  dy uses its own view;
+ * dy_lc0 = logical channel of dy that corresponds to x's physical channel c_off. */
+int cvd_bn_bwd_reduce(const float* x, int x_ctotal, int x_coff,
+                      const float* dy, int dy_ctotal, int dy_coff, int dy_n0, int dy_gap, int dy_lc0,
+                      const float* a, const float* b, const float* rstd, const float* mean,
+                      const float* gamma, const float* beta, int relu,
+                      long long npix, int C, void* scratch,
+                      float* bw, float* dgamma, float* dbeta, float* dbias, void* stream);
+
+/* nn.AvgPool2d(2) (hourglass.py:70,95,113,138) of relu?(a x + b) read through a view -> plain
+ * (N,H/2,W/2,C); backward: dx (plain N,H,W,C) (+)= 0.25 * dp. */
+int cvd_pool_fwd(const float* x, int c_total, int c_off, int n0, int gap, const float* a, const float* b,
+                 int relu, float* p, int N, int H, int W, int C, void* stream);
+int cvd_pool_bwd(const float* dp, float* dx, int accumulate, int N, int H, int W, int C, void* stream);
+
+/* ChannelsN.forward (hourglass.py:81,106,131,156): z = relu(a1 x1 + b1) + up2x(relu(a2 x2 + b2)),
+ * nn.UpsamplingBilinear2d(scale_factor=2) (align_corners=True); x2 is (N,H/2,W/2,.).  z plain.
+ * Backward of the upsample half: dy2 = up2x^T(dz) (gather form, deterministic); dy1 == dz. */
+int cvd_merge_up_fwd(const float* x1, int ct1, int c01, int n01, int gap1, const float* a1, const float* b1,
+                     const float* x2, int ct2, int c02, int n02, int gap2, const float* a2, const float* b2,
+                     float* z, int N, int H, int W, int C, void* stream);
+int cvd_up2x_bwd(const float* dz, float* dy2, int N, int H, int W, int C, void* stream);
+
+/* (N,3,H,W) BGR image (DepthModel.forward input, depth_model.py:12-16) -> (N,H,W,4), 4th channel 0 */
+int cvd_image_to_nhwc4(const float* img_nchw, float* out, int N, int H, int W, void* stream);
+
+/* exp() backward of mannequin_challenge_model.py:66: out4[i] = (grad_depth[i]*depth[i], 0, 0, 0);
+ * dbias (pred_layer.bias gradient, 1 float, accumulated) may be NULL. */
+int cvd_dlogdepth(const float* grad_depth, const float* depth, float* out4, long long n, float* dbias, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

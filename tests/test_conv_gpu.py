@@ -135,7 +135,7 @@ def test_conv_bn_backward_on_load():
 
 def test_conv_full_size_layer_linearity():
     """BASELINE config-2 size (8 frames 224x384, the heaviest layer 64->16 11x11): conv(x1+x2) == conv(x1)+conv(x2)
-    and agreement with torch on a probe crop."""
+    and agreement with torch (fp64) on a top-left probe crop."""
     cin, cout, k, N, H, W = 64, 16, 11, 8, 224, 384
     g = torch.Generator(device=DEV).manual_seed(0)
     x1 = torch.rand(N, cin, H, W, device=DEV, generator=g) - 0.5
@@ -143,5 +143,59 @@ def test_conv_full_size_layer_linearity():
     w = (torch.rand(cout, cin, k, k, device=DEV, generator=g) - 0.5) * 0.05
     y1 = run_conv(x1, w, None, k); y2 = run_conv(x2, w, None, k); y12 = run_conv(x1 + x2, w, None, k)
     assert (y12 - (y1 + y2)).abs().max().item() <= 1e-4 * y12.abs().max().item()
-    ref = F.conv2d(x1[:1].double(), w.double(), None, padding=5)
-    assert (y1[:1].permute(0, 3, 1, 2).double() - ref).abs().max().item() <= 6e-5 * ref.abs().max().item()
+    ref = F.conv2d(x1[7:, :, :40, :56].double(), w.double(), None, padding=5)[:, :, :32, :48]
+    got = y1[7:, :32, :48].permute(0, 3, 1, 2).double()
+    assert (got - ref).abs().max().item() <= 6e-5 * ref.abs().max().item()
+
+
+WG_SHAPES = [
+    # cin, cout, k, N, H, W
+    (64, 16, 11, 1, 32, 48),       # M = Cin(64), N = Cout(16), 6 tap groups
+    (32, 32, 3, 2, 32, 32),        # M=64 padded from 32
+    (32, 64, 5, 1, 20, 28),        # M = Cout, ragged H/W
+    (64, 64, 7, 1, 16, 32),        # 8 taps per group
+    (128, 208, 1, 1, 32, 48),      # fused 1x1: M = Cout(208 -> 2 x 128), N = Cin
+    (256, 160, 1, 1, 16, 32),      # M = Cin (2 x 128)
+    (3, 128, 7, 1, 32, 48),        # first layer (image, 4-channel tensor)
+    (64, 1, 3, 1, 32, 48),         # pred layer (G has 1 channel in a 4-channel tensor)
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,N,H,W", WG_SHAPES)
+def test_conv_wgrad_matches_autograd(cin, cout, k, N, H, W):
+    from consistent_depth_b200 import ops
+    x = rnd(1 + cin, (N, cin, H, W))
+    gy = rnd(2 + cout, (N, cout, H, W))
+    w = torch.zeros(cout, cin, k, k, device=DEV, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double(), w, None, padding=(k - 1) // 2).backward(gy.double())
+    cx, cg = (cin + 3) // 4 * 4, (cout + 3) // 4 * 4
+    xb = torch.zeros(N, H, W, cx, device=DEV); xb[..., :cin] = nhwc(x)
+    gb = torch.zeros(N, H, W, cg, device=DEV); gb[..., :cout] = nhwc(gy)
+    dw = torch.zeros(cout, cin, k, k, device=DEV)
+    ops.conv_wgrad(ops.make_src(ops.View(gb)), ops.make_src(ops.View(xb)), dw, N, H, W, cin, cout, k, 3)
+    torch.cuda.synchronize()
+    err = (dw.double() - w.grad).abs().max().item()
+    assert err <= 6e-5 * w.grad.abs().max().item(), (err, w.grad.abs().max().item())
+
+
+def test_conv_wgrad_with_transforms_on_load():
+    from consistent_depth_b200 import ops
+    cin, cout, k, N, H, W = 32, 32, 3, 1, 16, 32
+    xin_raw = rnd(3, (N, cin, H, W)); ax = rnd(4, (cin,), 0.5, 1.5); bx = rnd(5, (cin,), -0.5, 0.5)
+    xraw = rnd(6, (N, cout, H, W)); dy = rnd(7, (N, cout, H, W))
+    a = rnd(8, (cout,), 0.5, 1.5); b = rnd(9, (cout,), -0.3, 0.3)
+    c0 = rnd(10, (cout,), 0.5, 1.5); c1 = rnd(11, (cout,), -0.1, 0.1); c2 = rnd(12, (cout,), -0.1, 0.1)
+    bw = torch.stack([c0, c1, c2, torch.zeros_like(c0)], 1).contiguous()
+    v = lambda t: t.double().view(1, -1, 1, 1)
+    xin = F.relu(xin_raw.double() * v(ax) + v(bx))
+    yv = xraw.double() * v(a) + v(b)
+    g = torch.where(yv > 0, dy.double(), torch.zeros_like(yv))
+    dxraw = v(c0) * g - v(c1) - v(c2) * yv
+    w = torch.zeros(cout, cin, k, k, device=DEV, dtype=torch.float64, requires_grad=True)
+    F.conv2d(xin, w, None, padding=1).backward(dxraw)
+    dw = torch.zeros(cout, cin, k, k, device=DEV)
+    gsrc = ops.make_src(ops.View(nhwc(xraw)), a, b, True, dy=ops.View(nhwc(dy)), bw=bw)
+    xsrc = ops.make_src(ops.View(nhwc(xin_raw)), ax, bx, True)
+    ops.conv_wgrad(gsrc, xsrc, dw, N, H, W, cin, cout, k, 3)
+    torch.cuda.synchronize()
+    assert (dw.double() - w.grad).abs().max().item() <= 6e-5 * w.grad.abs().max().item()
