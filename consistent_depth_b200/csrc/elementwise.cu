@@ -207,9 +207,10 @@ pool_fwd_kernel(const float* __restrict__ x, int ct, int c0, int n0, int gap, co
   }
 }
 
-// dx[n, y, x, c] (+)= 0.25 dp[n, y/2, x/2, c]   (both plain, C channels)
+// dx[n, y, x, view(c)] (+)= 0.25 dp[n, y/2, x/2, c]   (dp plain C channels, dx through a channel view)
 __global__ void __launch_bounds__(256)
-pool_bwd_kernel(const float* __restrict__ dp, float* __restrict__ dx, int accumulate, int N, int H, int W, int C)
+pool_bwd_kernel(const float* __restrict__ dp, float* __restrict__ dx, int ct, int c0, int n0, int gap,
+                int accumulate, int N, int H, int W, int C)
 {
   const int cq = C >> 2, Ho = H >> 1, Wo = W >> 1;
   const long long total = (long long)N * H * W * cq;
@@ -221,7 +222,7 @@ pool_bwd_kernel(const float* __restrict__ dp, float* __restrict__ dx, int accumu
       g = __ldg(reinterpret_cast<const float4*>(dp) + (((long long)n * Ho + (yy >> 1)) * Wo + (xx >> 1)) * cq + q);
       g.x *= 0.25f; g.y *= 0.25f; g.z *= 0.25f; g.w *= 0.25f;
     }
-    float4* o = reinterpret_cast<float4*>(dx) + i;
+    float4* o = reinterpret_cast<float4*>(dx + (((long long)n * H + yy) * W + xx) * ct + vphys(4 * q, c0, n0, gap));
     if (accumulate) { const float4 old = *o; g.x += old.x; g.y += old.y; g.z += old.z; g.w += old.w; }
     *o = g;
   }
@@ -263,10 +264,13 @@ merge_up_fwd_kernel(const float* __restrict__ x1, int ct1, int c01, int n01, int
   }
 }
 
-// dy2[n, ys, xs, c] = sum over the (<= 4x4) fine pixels whose bilinear footprint touches (ys, xs).
-// Gather form of the transposed upsample: deterministic, no atomics.
+// Backward of z = y1 + up2x(y2) for plain dz (N,H,W,C):
+//   dy2[n, ys, xs, view2(c)] = sum over the (<= 4x4) fine pixels whose bilinear footprint touches (ys, xs)
+//                              (gather form of the transposed upsample: deterministic, no atomics)
+//   dy1[n, y, x, view1(c)]   = dz[n, y, x, c]  (the thread also forwards its 2x2 block; dy1 may be NULL)
 __global__ void __launch_bounds__(256)
-up2x_bwd_kernel(const float* __restrict__ dz, float* __restrict__ dy2, int N, int H, int W, int C)
+up2x_bwd_kernel(const float* __restrict__ dz, float* __restrict__ dy2, int ct2, int c02, int n02, int gap2,
+                float* __restrict__ dy1, int ct1, int c01, int n01, int gap1, int acc1, int N, int H, int W, int C)
 {
   const int cq = C >> 2, Hs = H >> 1, Ws = W >> 1;
   const float sy = Hs > 1 ? (float)(Hs - 1) / (float)(H - 1) : 0.f;
@@ -275,7 +279,6 @@ up2x_bwd_kernel(const float* __restrict__ dz, float* __restrict__ dy2, int N, in
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int q = (int)(i % cq); long long r = i / cq;
     const int xs = (int)(r % Ws); r /= Ws; const int ys = (int)(r % Hs); const int n = (int)(r / Hs);
-    // candidate fine rows: those with floor(sy*y) in {ys-1, ys}
     const int ylo = max(0, 2 * ys - 3), yhi = min(H - 1, 2 * ys + 3);
     const int xlo = max(0, 2 * xs - 3), xhi = min(W - 1, 2 * xs + 3);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -298,7 +301,20 @@ up2x_bwd_kernel(const float* __restrict__ dz, float* __restrict__ dy2, int N, in
         acc.x = fmaf(wgt, g.x, acc.x); acc.y = fmaf(wgt, g.y, acc.y); acc.z = fmaf(wgt, g.z, acc.z); acc.w = fmaf(wgt, g.w, acc.w);
       }
     }
-    reinterpret_cast<float4*>(dy2)[i] = acc;
+    *reinterpret_cast<float4*>(dy2 + (((long long)n * Hs + ys) * Ws + xs) * ct2 + vphys(4 * q, c02, n02, gap2)) = acc;
+    if (dy1) {
+      const int pc1 = vphys(4 * q, c01, n01, gap1);
+#pragma unroll
+      for (int dyy = 0; dyy < 2; ++dyy)
+#pragma unroll
+        for (int dxx = 0; dxx < 2; ++dxx) {
+          const long long pix = ((long long)n * H + 2 * ys + dyy) * W + 2 * xs + dxx;
+          float4 g = __ldg(reinterpret_cast<const float4*>(dz) + pix * cq + q);
+          float4* o = reinterpret_cast<float4*>(dy1 + pix * ct1 + pc1);
+          if (acc1) { const float4 old = *o; g.x += old.x; g.y += old.y; g.z += old.z; g.w += old.w; }
+          *o = g;
+        }
+    }
   }
 }
 
@@ -402,11 +418,13 @@ extern "C" int cvd_pool_fwd(const float* x, int c_total, int c_off, int n0, int 
   return 0;
 }
 
-extern "C" int cvd_pool_bwd(const float* dp, float* dx, int accumulate, int N, int H, int W, int C, void* stream)
+extern "C" int cvd_pool_bwd(const float* dp, float* dx, int c_total, int c_off, int n0, int gap, int accumulate,
+                            int N, int H, int W, int C, void* stream)
 {
   CVD_CHECK_ARG(dp && dx, "cvd_pool_bwd: null pointer");
-  CVD_CHECK_ARG((C & 3) == 0, "cvd_pool_bwd: C %% 4 required");
-  pool_bwd_kernel<<<ew_grid((long long)N * H * W * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dp, dx, accumulate, N, H, W, C);
+  CVD_CHECK_ARG((C & 3) == 0 && (c_total & 3) == 0 && (c_off & 3) == 0 && (gap & 3) == 0, "cvd_pool_bwd: 4-channel alignment required");
+  pool_bwd_kernel<<<ew_grid((long long)N * H * W * (C / 4)), 256, 0, (cudaStream_t)stream>>>(
+      dp, dx, c_total, c_off, n0 > 0 ? n0 : (1 << 30), gap, accumulate, N, H, W, C);
   CVD_LAUNCH_OK("pool_bwd_kernel");
   return 0;
 }
@@ -423,11 +441,14 @@ extern "C" int cvd_merge_up_fwd(const float* x1, int ct1, int c01, int n01, int 
   return 0;
 }
 
-extern "C" int cvd_up2x_bwd(const float* dz, float* dy2, int N, int H, int W, int C, void* stream)
+extern "C" int cvd_merge_up_bwd(const float* dz, float* dy2, int ct2, int c02, int n02, int gap2,
+                                float* dy1, int ct1, int c01, int n01, int gap1, int accumulate1,
+                                int N, int H, int W, int C, void* stream)
 {
-  CVD_CHECK_ARG(dz && dy2, "cvd_up2x_bwd: null pointer");
-  CVD_CHECK_ARG((C & 3) == 0 && (H & 1) == 0 && (W & 1) == 0, "cvd_up2x_bwd: C %% 4, even H, W required");
-  up2x_bwd_kernel<<<ew_grid((long long)N * (H / 2) * (W / 2) * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dz, dy2, N, H, W, C);
+  CVD_CHECK_ARG(dz && dy2, "cvd_merge_up_bwd: null pointer");
+  CVD_CHECK_ARG((C & 3) == 0 && (H & 1) == 0 && (W & 1) == 0, "cvd_merge_up_bwd: C %% 4, even H, W required");
+  up2x_bwd_kernel<<<ew_grid((long long)N * (H / 2) * (W / 2) * (C / 4)), 256, 0, (cudaStream_t)stream>>>(
+      dz, dy2, ct2, c02, n02 > 0 ? n02 : (1 << 30), gap2, dy1, ct1, c01, n01 > 0 ? n01 : (1 << 30), gap1, accumulate1, N, H, W, C);
   CVD_LAUNCH_OK("up2x_bwd_kernel");
   return 0;
 }

@@ -110,9 +110,10 @@ def pool_fwd(xv, a, b, relu, p, N, H, W, Cn):
                                        1 if relu else 0, _lib.ptr(p), N, H, W, Cn, _lib.stream()), "cvd_pool_fwd")
 
 
-def pool_bwd(dp, dx, accumulate, N, H, W, Cn):
-    _lib.check(_lib.lib().cvd_pool_bwd(_lib.ptr(dp), _lib.ptr(dx), 1 if accumulate else 0, N, H, W, Cn,
-                                       _lib.stream()), "cvd_pool_bwd")
+def pool_bwd(dp, dxv, accumulate, N, H, W, Cn):
+    """dxv: View of the full-resolution gradient buffer."""
+    _lib.check(_lib.lib().cvd_pool_bwd(_lib.ptr(dp), _lib.ptr(dxv.t), dxv.c_total, dxv.off, dxv.n0, dxv.gap,
+                                       1 if accumulate else 0, N, H, W, Cn, _lib.stream()), "cvd_pool_bwd")
 
 
 def merge_up_fwd(x1v, a1, b1, x2v, a2, b2, z, N, H, W, Cn):
@@ -121,8 +122,17 @@ def merge_up_fwd(x1v, a1, b1, x2v, a2, b2, z, N, H, W, Cn):
                                            _lib.ptr(z), N, H, W, Cn, _lib.stream()), "cvd_merge_up_fwd")
 
 
-def up2x_bwd(dz, dy2, N, H, W, Cn):
-    _lib.check(_lib.lib().cvd_up2x_bwd(_lib.ptr(dz), _lib.ptr(dy2), N, H, W, Cn, _lib.stream()), "cvd_up2x_bwd")
+def merge_up_bwd(dz, dy2v, dy1v, accumulate1, N, H, W, Cn):
+    """dz plain (N,H,W,Cn); dy2v: View at half resolution; dy1v: View at full resolution or None."""
+    L = _lib.lib()
+    if dy1v is None:
+        rc = L.cvd_merge_up_bwd(_lib.ptr(dz), _lib.ptr(dy2v.t), dy2v.c_total, dy2v.off, dy2v.n0, dy2v.gap,
+                                None, 0, 0, 0, 0, 0, N, H, W, Cn, _lib.stream())
+    else:
+        rc = L.cvd_merge_up_bwd(_lib.ptr(dz), _lib.ptr(dy2v.t), dy2v.c_total, dy2v.off, dy2v.n0, dy2v.gap,
+                                _lib.ptr(dy1v.t), dy1v.c_total, dy1v.off, dy1v.n0, dy1v.gap, 1 if accumulate1 else 0,
+                                N, H, W, Cn, _lib.stream())
+    _lib.check(rc, "cvd_merge_up_bwd")
 
 
 def image_to_nhwc4(img, out, N, H, W):

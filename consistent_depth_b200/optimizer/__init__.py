@@ -13,8 +13,15 @@ import torch
 from .. import _lib
 
 
+class FlatParamList(list):
+    """A parameter list whose tensors are already views of one flat buffer (`.flat`, with `.grad_flat`)."""
+    flat = None
+    grad_flat = None
+
+
 class FusedAdam:
     def __init__(self, params, lr, betas=(0.9, 0.999), eps=1e-8):
+        adopt = params if isinstance(params, FlatParamList) and params.flat is not None else None
         self.params = [p for p in params]
         if not self.params:
             raise ValueError("optimizer got an empty parameter list")
@@ -22,6 +29,14 @@ class FusedAdam:
         if dev.type != "cuda":
             raise _lib.CvdError("FusedAdam needs CUDA parameters (no CPU path)")
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.grad_scale = 1.0
+        self.loss_flag = None       # optional device scalar; NaN => step skipped on device
+        if adopt is not None:       # engine-owned flat storage: no re-homing
+            self.flat, self.grad_flat, self.numel = adopt.flat, adopt.grad_flat, adopt.flat.numel()
+            self.exp_avg = torch.zeros_like(self.flat)
+            self.exp_avg_sq = torch.zeros_like(self.flat)
+            self.state = torch.zeros(4, dtype=torch.int32, device=dev)
+            return
         sizes = [p.numel() for p in self.params]
         offs, tot = [], 0
         for n in sizes:
@@ -38,8 +53,6 @@ class FusedAdam:
             view.copy_(p.data)
             p.data = view
             p.grad = self.grad_flat[o:o + n].view(p.shape)
-        self.grad_scale = 1.0
-        self.loss_flag = None       # optional device scalar; NaN => step skipped on device
 
     def zero_grad(self, set_to_none=False):
         self.grad_flat.zero_()

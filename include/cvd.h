@@ -185,18 +185,22 @@ int cvd_bn_bwd_reduce(const float* x, int x_ctotal, int x_coff,
                       float* bw, float* dgamma, float* dbeta, float* dbias, void* stream);
 
 /* nn.AvgPool2d(2) (hourglass.py:70,95,113,138) of relu?(a x + b) read through a view -> plain
- * (N,H/2,W/2,C); backward: dx (plain N,H,W,C) (+)= 0.25 * dp. */
+ * (N,H/2,W/2,C); backward: dx (N,H,W through a channel view) (+)= 0.25 * dp. */
 int cvd_pool_fwd(const float* x, int c_total, int c_off, int n0, int gap, const float* a, const float* b,
                  int relu, float* p, int N, int H, int W, int C, void* stream);
-int cvd_pool_bwd(const float* dp, float* dx, int accumulate, int N, int H, int W, int C, void* stream);
+int cvd_pool_bwd(const float* dp, float* dx, int c_total, int c_off, int n0, int gap, int accumulate,
+                 int N, int H, int W, int C, void* stream);
 
 /* ChannelsN.forward (hourglass.py:81,106,131,156): z = relu(a1 x1 + b1) + up2x(relu(a2 x2 + b2)),
  * nn.UpsamplingBilinear2d(scale_factor=2) (align_corners=True); x2 is (N,H/2,W/2,.).  z plain.
- * Backward of the upsample half: dy2 = up2x^T(dz) (gather form, deterministic); dy1 == dz. */
+ * Backward: dy2 (view, half res) = up2x^T(dz) (gather form, deterministic);
+ *           dy1 (view, full res, may be NULL) (+)= dz. */
 int cvd_merge_up_fwd(const float* x1, int ct1, int c01, int n01, int gap1, const float* a1, const float* b1,
                      const float* x2, int ct2, int c02, int n02, int gap2, const float* a2, const float* b2,
                      float* z, int N, int H, int W, int C, void* stream);
-int cvd_up2x_bwd(const float* dz, float* dy2, int N, int H, int W, int C, void* stream);
+int cvd_merge_up_bwd(const float* dz, float* dy2, int ct2, int c02, int n02, int gap2,
+                     float* dy1, int ct1, int c01, int n01, int gap1, int accumulate1,
+                     int N, int H, int W, int C, void* stream);
 
 /* (N,3,H,W) BGR image (DepthModel.forward input, depth_model.py:12-16) -> (N,H,W,4), 4th channel 0 */
 int cvd_image_to_nhwc4(const float* img_nchw, float* out, int N, int H, int W, void* stream);

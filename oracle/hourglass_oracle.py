@@ -120,13 +120,16 @@ def _bn_train(x, prefix, P, buffers, affine, momentum=0.1, eps=1e-5):
     return F.batch_norm(x, rm, rv, w, b, True, momentum, eps)
 
 
-def hourglass_forward(x, P, buffers=None):
+def hourglass_forward(x, P, buffers=None, capture=None):
     """x (N,3,H,W) -> log-depth (N,1,H,W).  P: dict key->tensor (requires_grad for training),
-    buffers: dict of BN running stats, updated in place (may be {} to ignore)."""
+    buffers: dict of BN running stats, updated in place (may be {} to ignore);
+    capture: optional dict filled with every conv's raw (pre-BatchNorm) output, keyed by conv prefix."""
     buffers = {} if buffers is None else buffers
 
     def conv_bn_relu(x, prefix_conv, prefix_bn, pad, affine=False):
         y = F.conv2d(x, P[prefix_conv + ".weight"], P[prefix_conv + ".bias"], padding=pad)
+        if capture is not None:
+            capture[prefix_conv] = y.detach()
         return F.relu(_bn_train(y, prefix_bn, P, buffers, affine))
 
     def inception(x, prefix, cfg):
@@ -158,11 +161,11 @@ def hourglass_forward(x, P, buffers=None):
     return F.conv2d(y, P["pred_layer.weight"], P["pred_layer.bias"], padding=1)
 
 
-def estimate_depth(images, P, buffers=None):
+def estimate_depth(images, P, buffers=None, capture=None):
     """mannequin_challenge_model.py:52-69: (...,3,H,W) -> (...,H,W) depth = exp(log-depth)."""
     shape = images.shape
     C, H, W = shape[-3:]
-    pred = hourglass_forward(images.reshape(-1, C, H, W), P, buffers)
+    pred = hourglass_forward(images.reshape(-1, C, H, W), P, buffers, capture)
     pred = pred.reshape(shape[:-3] + pred.shape[-2:])     # X1HW -> (...,H,W)
     return torch.exp(pred)
 

@@ -90,9 +90,12 @@ def test_pool_and_merge_up_forward_backward():
     y2r = y2.detach().requires_grad_(True)
     F.interpolate(y2r, scale_factor=2, mode="bilinear", align_corners=True).backward(dz.double())
     dy2 = torch.empty(N, H // 2, W // 2, C, device=DEV)
-    ops.up2x_bwd(nhwc(dz), dy2, N, H, W, C)
+    dzb = nhwc(dz)
+    dy1b = torch.full((N, H, W, 48), 3.0, device=DEV)
+    ops.merge_up_bwd(dzb, ops.View(dy2), ops.View(dy1b, 0, 16, 16), True, N, H, W, C)
     torch.cuda.synchronize()
     assert (nchw(dy2).double() - y2r.grad).abs().max().item() <= 1e-5
+    assert torch.equal(dy1b[..., idx], dzb + 3.0) and (dy1b[..., 16:32] == 3.0).all()
     # pool
     p = torch.empty(N, H // 2, W // 2, C, device=DEV)
     ops.pool_fwd(v1, a1, b1, True, p, N, H, W, C)
@@ -101,7 +104,7 @@ def test_pool_and_merge_up_forward_backward():
     assert (nchw(p).double() - refp).abs().max().item() <= 1e-5
     dp = rnd(8, (N, C, H // 2, W // 2))
     dx = torch.full((N, H, W, C), 2.0, device=DEV)
-    ops.pool_bwd(nhwc(dp), dx, True, N, H, W, C)
+    ops.pool_bwd(nhwc(dp), ops.View(dx), True, N, H, W, C)
     yy = y1.detach().requires_grad_(True)
     F.avg_pool2d(yy, 2).backward(dp.double())
     torch.cuda.synchronize()

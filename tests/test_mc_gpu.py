@@ -1,0 +1,123 @@
+"""GPU: the sm_100a hourglass engine (forward + hand-written backward + fused Adam) vs the oracle and the
+reference-generated goldens (tests/golden/hourglass_small.npz, finetune_steps.npz).
+
+Stated tolerances (north_star: per-pixel depth L1 <= 1e-3 vs reference; bf16x3-split tensor-core convs):
+  forward: every conv's raw output max-abs err <= 2e-3 of its max magnitude; depth mean relative L1 <= 1e-3
+  backward: gradient norms within 5 %, selected gradient tensors max-abs err <= 6 % of their max (the fp32 and fp64
+            oracles themselves differ by up to 1e-3 in these norms: error amplification ~2000x at random init)
+  3 fine-tune steps: loss trajectory rel 2e-3, final depth mean relative L1 <= 1e-3 x 3
+"""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth, hourglass_oracle as ho, consistency_oracle as co
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def make_model(seed):
+    from consistent_depth_b200.monodepth.mannequin_challenge_model import MannequinChallengeModel
+    sd = {k: torch.tensor(np.asarray(v)) for k, v in ho.mc_init_state(seed).items()}
+    return MannequinChallengeModel(state_dict=sd)
+
+
+def metadata(batch):
+    t = lambda a: torch.tensor(a, device=DEV)
+    return {"extrinsics": t(batch["extrinsics"]), "intrinsics": t(batch["intrinsics"]),
+            "geometry_consistency": {"indices": t(batch["indices"]), "flows": [t(f) for f in batch["flows"]],
+                                     "masks": [t(m) for m in batch["masks"]]}}
+
+
+def test_forward_layerwise_and_backward_match_reference(golden_dir):
+    from consistent_depth_b200.loss.joint_loss import JointLoss
+    g = np.load(os.path.join(golden_dir, "hourglass_small.npz"))
+    seed, H, W = 21, 32, 48
+    model = make_model(seed).train()
+    batch = synth.make_pair_batch(seed, [(0, 1)], H, W)
+    images = torch.tensor(batch["images"], device=DEV)
+    depth = model(images, None)
+    torch.cuda.synchronize()
+    # layer-by-layer against the oracle (CPU fp32)
+    P, buffers = ho.to_torch(ho.mc_init_state(seed))
+    cap = {}
+    with torch.no_grad():
+        ho.estimate_depth(torch.tensor(batch["images"]), P, buffers, cap)
+    eng = model.engine(2, H, W)
+    worst = (0.0, None)
+    for key, ref in cap.items():
+        if key not in eng.raw_outputs:          # fused 1x1: members live at channel offsets of the first one
+            continue
+    for key, (buf, off, cout) in eng.raw_outputs.items():
+        if key == "pred_layer":
+            continue
+        if key.endswith("convs.0.0"):           # fused 1x1 GEMM: o0 | a1 | a2 | a3
+            pre = key[:-len("convs.0.0")]
+            ref = torch.cat([cap[f"{pre}convs.{i}.0"] for i in range(4)], 1)
+        else:
+            ref = cap[key]
+        got = buf[..., off:off + cout].permute(0, 3, 1, 2).cpu()
+        err = (got - ref).abs().max().item() / ref.abs().max().item()
+        if err > worst[0]:
+            worst = (err, key)
+        assert err <= 2e-3, f"{key}: raw conv output rel err {err:.3e}"
+    d = depth.detach().cpu().numpy()
+    rel = np.abs(d - g["depth"]) / g["depth"]
+    print(f"worst layer err {worst}; depth mean rel L1 {rel.mean():.3e} max {rel.max():.3e}")
+    assert rel.mean() <= 1e-3
+    # BN running statistics (train-mode side effect)
+    sd = model.state_dict()
+    for k in g.files:
+        if k.startswith("buf::"):
+            np.testing.assert_allclose(sd[k[5:]].cpu().numpy(), g[k], rtol=2e-3, atol=2e-4)
+    # loss + backward through the reference-style API
+    opt = types.SimpleNamespace(lambda_view_baseline=0.1, lambda_reprojection=1.0, lambda_parameter=0)
+    params = model.parameters()
+    model.P.grad_flat.zero_()
+    loss, _ = JointLoss(opt)(depth, metadata(batch))
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), g["loss"], rtol=2e-3)
+    loss.backward()
+    torch.cuda.synchronize()
+    named = dict(model.P.named_parameters())
+    names = [str(n) for n in g["grad_names"]]
+    norms = np.array([float(model.P._g(k).double().norm()) for k in names])
+    big = g["grad_norms"] > 1e-4
+    np.testing.assert_allclose(norms[big], g["grad_norms"][big], rtol=5e-2)   # fp32-vs-fp64 oracle already differs by up to 1e-3 here: ~2000x error amplification at random init, BN over 2 frames
+    for k in g.files:
+        if k.startswith("grad::"):
+            ref = g[k]
+            got = model.P._g(k[6:]).cpu().numpy()
+            assert np.abs(got - ref).max() <= 6e-2 * np.abs(ref).max(), k
+
+
+def test_three_finetune_steps_match_reference(golden_dir):
+    from consistent_depth_b200.loss.joint_loss import JointLoss
+    from consistent_depth_b200 import optimizer
+    g = np.load(os.path.join(golden_dir, "finetune_steps.npz"))
+    seed, H, W = 41, 32, 48
+    model = make_model(seed).train()
+    batch = synth.make_pair_batch(seed, [(0, 2)], H, W)
+    images = torch.tensor(batch["images"], device=DEV)
+    meta = metadata(batch)
+    crit = JointLoss(types.SimpleNamespace(lambda_view_baseline=0.1, lambda_reprojection=1.0, lambda_parameter=0))
+    opt = optimizer.create("Adam", model.parameters(), 4e-4, betas=(0.9, 0.999))
+    losses = []
+    for _ in range(3):          # depth_fine_tuning.py:264-283
+        depth = model(images, meta)
+        opt.zero_grad()
+        loss, _m = crit(depth, meta, parameters=model.parameters())
+        loss.backward()
+        opt.step()
+        losses.append(float(loss[0]))
+    with torch.no_grad():
+        depth = model(images, None)
+    torch.cuda.synchronize()
+    print("losses", losses, "ref", g["losses"])
+    np.testing.assert_allclose(losses, g["losses"], rtol=2e-3)
+    rel = np.abs(depth.cpu().numpy() - g["final_depth"]) / g["final_depth"]
+    print(f"final depth mean rel L1 {rel.mean():.3e}")
+    assert rel.mean() <= 3e-3
