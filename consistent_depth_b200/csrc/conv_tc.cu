@@ -27,6 +27,7 @@
 // (tcgen05.ld -> +bias / exp -> NHWC global stores).
 #include "cvd_common.cuh"
 #include "tc_common.cuh"
+#include "fill.cuh"
 
 namespace {
 
@@ -36,11 +37,7 @@ constexpr int kMaxStages = 8;
 constexpr int kGroupCh = 64;          // channels per activation group resident in one A slot
 
 struct ConvArgs {
-  // source view
-  const float* x; const float* dy; const float* a; const float* b; const float4* bw;
-  int x_ct, x_c0, x_n0, x_gap;
-  int dy_ct, dy_c0, dy_n0, dy_gap;
-  int relu, mode, cin_valid;
+  fillns::SrcView src;               // source view + transform
   // weights / bias
   const uint8_t* wp; const float* bias;
   // destination view
@@ -57,72 +54,6 @@ struct ConvArgs {
 };
 
 __device__ __forceinline__ int view_phys(int c, int c0, int n0, int gap) { return c0 + c + (c >= n0 ? gap : 0); }
-
-// ------------------------------------------------------------------ activation producer
-// Fills one A slot with channel group `g` of the halo tile whose top-left output pixel is (oy, ox).
-__device__ __forceinline__ void fill_slot(const ConvArgs& p, uint8_t* slot, int g, int n, int oy, int ox, int tid)
-{
-  const int gch = min(p.gchunks, (p.cin - g * kGroupCh) >> 3);   // 8-channel chunks in this group
-  const int npix = p.HP * p.WP;
-  const int total = npix * gch;
-  const int lo_off = p.gchunks * p.plane_bytes;        // lo planes follow the (max-sized) hi plane set
-  const size_t img_off = (size_t)n * p.H * p.W;
-  for (int it = tid; it < total; it += kProducerThreads) {
-    const int c8 = it % gch;                           // chunk fastest: consecutive threads read consecutive 32 B
-    const int hp = it / gch;
-    const int hy = hp / p.WP, hx = hp - hy * p.WP;
-    const int iy = oy + hy - p.pad, ix = ox + hx - p.pad;
-    const int cl = g * kGroupCh + c8 * 8;              // logical first channel of the chunk
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.f;
-    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W && cl < p.cin_valid) {
-      const size_t pix = img_off + (size_t)iy * p.W + ix;
-      const int pc = view_phys(cl, p.x_c0, p.x_n0, p.x_gap);
-      const float* xp = p.x + pix * p.x_ct + pc;
-      const bool second = cl + 4 < p.cin_valid;
-      float4 x0 = __ldg(reinterpret_cast<const float4*>(xp));
-      float4 x1 = second ? __ldg(reinterpret_cast<const float4*>(xp + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-      if (p.a) {
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 a0 = __ldg(reinterpret_cast<const float4*>(p.a + pc)), a1 = second ? __ldg(reinterpret_cast<const float4*>(p.a + pc + 4)) : z4;
-        float4 b0 = __ldg(reinterpret_cast<const float4*>(p.b + pc)), b1 = second ? __ldg(reinterpret_cast<const float4*>(p.b + pc + 4)) : z4;
-        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) xv[i] = fmaf(av[i], xv[i], bv[i]);
-      }
-      if (p.mode == CVD_XF_AFFINE) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = p.relu ? fmaxf(xv[i], 0.f) : xv[i];
-      } else {
-        // BatchNorm(+ReLU) backward on load: y = a x + b ; g = dy * [y > 0] ; dx = c0 g - c1 - c2 y
-        const int dc = view_phys(cl, p.dy_c0, p.dy_n0, p.dy_gap);
-        const float* dp = p.dy + pix * p.dy_ct + dc;
-        float4 d0 = __ldg(reinterpret_cast<const float4*>(dp));
-        float4 d1 = second ? __ldg(reinterpret_cast<const float4*>(dp + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (i >= 4 && !second) break;
-          const float4 c = __ldg(p.bw + pc + i);
-          const float gq = (!p.relu || xv[i] > 0.f) ? dv[i] : 0.f;
-          v[i] = c.x * gq - c.y - c.z * xv[i];
-        }
-      }
-      if (!second) {
-#pragma unroll
-        for (int i = 4; i < 8; ++i) v[i] = 0.f;
-      }
-    }
-    uint4 hi, lo;
-    tc::split8(v, hi, lo);
-    uint8_t* dst = slot + (size_t)c8 * p.plane_bytes + (size_t)hp * 16;
-    *reinterpret_cast<uint4*>(dst) = hi;
-    if (p.nsplit == 3) *reinterpret_cast<uint4*>(dst + lo_off) = lo;
-  }
-}
 
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(kThreads, 1)
@@ -164,55 +95,58 @@ conv_tc_kernel(const ConvArgs p)
   const uint32_t tmem_base = *tmem_base_sh;
 
   const int taps = p.k * p.k;
-  const int MT = p.mtx * p.mty;
   const int kb_total = taps * (p.cin >> 4);                      // number of weight stages streamed
 
   if (warp == 0) {
-    // ============================ MMA issuer (one thread) ============================
-    if (lane == 0) {
-      const uint32_t idesc = tc::idesc_bf16(128, p.cout, 0, 0);
-      const uint32_t a_base = tc::smem_u32(a_slots), b_base = tc::smem_u32(b_stages);
-      const uint32_t lo_a = (uint32_t)p.gchunks * p.plane_bytes;      // hi -> lo plane offset inside a slot
-      const uint32_t lo_b = (uint32_t)p.cout * 32;                     // hi -> lo blob offset inside a stage
-      const uint32_t sbo_a = (uint32_t)p.WP * 16;
-      int stage = 0; uint32_t bphase = 0;
-      for (int g = 0; g < p.ngroups; ++g) {
-        const int slot = g % p.nslots;
-        tc::mbar_wait(&a_full[slot], (uint32_t)((g / p.nslots) & 1));
-        tc::tc_fence_after();
-        const uint32_t slot_addr = a_base + (uint32_t)slot * p.slot_bytes;
-        const int kbg = min(kGroupCh, p.cin - g * kGroupCh) >> 4;      // 16-channel k-blocks in this group
-        for (int tap = 0; tap < taps; ++tap) {
-          const int ky = tap / p.k, kx = tap - ky * p.k;
+    // ============================ MMA issuer ============================
+    // The whole warp walks the (uniform) loop nest; one elected lane issues the tcgen05 instructions.
+    const uint32_t idesc = tc::idesc_bf16(128, p.cout, 0, 0);
+    const uint32_t a_base = tc::smem_u32(a_slots), b_base = tc::smem_u32(b_stages);
+    const uint32_t lo_a = (uint32_t)p.gchunks * p.plane_bytes;      // hi -> lo plane offset inside a slot
+    const uint32_t lo_b = (uint32_t)p.cout * 32;                     // hi -> lo blob offset inside a stage
+    const uint64_t adesc0 = tc::smem_desc_base((uint32_t)p.plane_bytes, (uint32_t)p.WP * 16);
+    const uint64_t bdesc0 = tc::smem_desc_base(128, 256);
+    const bool split = p.nsplit == 3;
+    int stage = 0; uint32_t bphase = 0;
+    for (int g = 0; g < p.ngroups; ++g) {
+      const int slot = g % p.nslots;
+      tc::mbar_wait(&a_full[slot], (uint32_t)((g / p.nslots) & 1));
+      tc::tc_fence_after();
+      const uint32_t slot_addr = a_base + (uint32_t)slot * p.slot_bytes;
+      const int kbg = min(kGroupCh, p.cin - g * kGroupCh) >> 4;      // 16-channel k-blocks in this group
+      for (int ky = 0; ky < p.k; ++ky) {
+        for (int kx = 0; kx < p.k; ++kx) {
           for (int kb = 0; kb < kbg; ++kb) {
             tc::mbar_wait(&b_full[stage], bphase);
             tc::tc_fence_after();
             const uint32_t bs = b_base + (uint32_t)stage * p.stage_bytes;
-            const uint64_t bd_hi = tc::smem_desc(bs, 128, 256);
-            const uint64_t bd_lo = tc::smem_desc(bs + lo_b, 128, 256);
-            const bool first_k = (g == 0 && tap == 0 && kb == 0);
-            for (int my = 0; my < p.mty; ++my) {
-              for (int mx = 0; mx < p.mtx; ++mx) {
-                const uint32_t a_addr = slot_addr + (uint32_t)(2 * kb) * p.plane_bytes +
-                                        (uint32_t)(((my * 16 + ky) * p.WP) + kx + mx * 8) * 16;
-                const uint32_t d = tmem_base + (uint32_t)((my * p.mtx + mx) * p.cout);
-                const uint64_t ad_hi = tc::smem_desc(a_addr, (uint32_t)p.plane_bytes, sbo_a);
-                tc::umma_f16(d, ad_hi, bd_hi, idesc, first_k ? 0u : 1u);
-                if (p.nsplit == 3) {
-                  const uint64_t ad_lo = tc::smem_desc(a_addr + lo_a, (uint32_t)p.plane_bytes, sbo_a);
-                  tc::umma_f16(d, ad_lo, bd_hi, idesc, 1u);
-                  tc::umma_f16(d, ad_hi, bd_lo, idesc, 1u);
+            const uint64_t bd_hi = tc::smem_desc_at(bdesc0, bs), bd_lo = tc::smem_desc_at(bdesc0, bs + lo_b);
+            const uint32_t acc0 = (g | ky | kx | kb) ? 1u : 0u;
+            const uint32_t a_tap = slot_addr + (uint32_t)(2 * kb) * p.plane_bytes + (uint32_t)((ky * p.WP + kx) * 16);
+            if (tc::elect_one()) {
+              for (int my = 0; my < p.mty; ++my) {
+                for (int mx = 0; mx < p.mtx; ++mx) {
+                  const uint32_t a_addr = a_tap + (uint32_t)((my * 16 * p.WP + mx * 8) * 16);
+                  const uint32_t d = tmem_base + (uint32_t)((my * p.mtx + mx) * p.cout);
+                  const uint64_t ad_hi = tc::smem_desc_at(adesc0, a_addr);
+                  tc::umma_f16(d, ad_hi, bd_hi, idesc, acc0);
+                  if (split) {
+                    tc::umma_f16(d, tc::smem_desc_at(adesc0, a_addr + lo_a), bd_hi, idesc, 1u);
+                    tc::umma_f16(d, ad_hi, bd_lo, idesc, 1u);
+                  }
                 }
               }
+              tc::umma_commit(&b_empty[stage]);        // weight stage reusable once these MMAs retire
             }
-            tc::umma_commit(&b_empty[stage]);        // weight stage reusable once these MMAs retire
+            __syncwarp();
             if (++stage == p.nstages) { stage = 0; bphase ^= 1; }
           }
         }
-        tc::umma_commit(&a_empty[slot]);             // activation slot reusable
       }
-      tc::umma_commit(acc_full);                     // accumulators complete
+      if (tc::elect_one()) tc::umma_commit(&a_empty[slot]);   // activation slot reusable
+      __syncwarp();
     }
+    if (tc::elect_one()) tc::umma_commit(acc_full);           // accumulators complete
     __syncwarp();
   } else if (warp == 1) {
     // ============================ weight streamer ============================
@@ -234,7 +168,9 @@ conv_tc_kernel(const ConvArgs p)
     for (int g = 0; g < p.ngroups; ++g) {
       const int slot = g % p.nslots;
       if (g >= p.nslots) tc::mbar_wait(&a_empty[slot], (uint32_t)(((g / p.nslots) - 1) & 1));
-      fill_slot(p, a_slots + (size_t)slot * p.slot_bytes, g, n, oy, ox, tid);
+      fillns::fill_window(p.src, a_slots + (size_t)slot * p.slot_bytes, p.plane_bytes, p.gchunks * p.plane_bytes, p.nsplit,
+                          n, p.H, p.W, oy - p.pad, ox - p.pad, p.HP, p.WP, g * kGroupCh,
+                          min(p.gchunks, (p.cin - g * kGroupCh) >> 3), tid);
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&a_full[slot]);
     }
@@ -293,7 +229,6 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cin_w, int 
 {
   // logical GEMM dims: K-channels = cin_pad (multiple of 16), N = cout_pad (multiple of 16)
   const int taps = k * k;
-  const int ngroups = (cin_pad + kGroupCh - 1) / kGroupCh;
   const int stage_bytes = cout_pad * 32 * (nsplit == 3 ? 2 : 1);
   const long long total = (long long)cin_pad * cout_pad * taps;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -361,11 +296,12 @@ extern "C" int cvd_conv_fwd(const cvd_src_t* src, const void* packed_w, const fl
                 "cvd_conv_fwd: source view must be 4-channel aligned");
   CVD_CHECK_ARG((dst->c_total & 3) == 0 || dst->c_total == 1, "cvd_conv_fwd: destination channel stride must be a multiple of 4 (or 1)");
   ConvArgs p{};
-  p.x = src->x; p.dy = src->dy; p.a = src->a; p.b = src->b; p.bw = reinterpret_cast<const float4*>(src->bw);
-  p.x_ct = src->c_total; p.x_c0 = src->c_off; p.x_n0 = src->n0 > 0 ? src->n0 : (1 << 30); p.x_gap = src->gap;
-  p.dy_ct = src->dy_ctotal; p.dy_c0 = src->dy_coff; p.dy_n0 = src->dy_n0 > 0 ? src->dy_n0 : (1 << 30); p.dy_gap = src->dy_gap;
-  p.relu = src->relu; p.mode = src->mode;
-  p.cin_valid = round_up(cin, 4);
+  fillns::SrcView& v = p.src;
+  v.x = src->x; v.dy = src->dy; v.a = src->a; v.b = src->b; v.bw = reinterpret_cast<const float4*>(src->bw);
+  v.ct = src->c_total; v.c0 = src->c_off; v.n0 = src->n0 > 0 ? src->n0 : (1 << 30); v.gap = src->gap;
+  v.dy_ct = src->dy_ctotal; v.dy_c0 = src->dy_coff; v.dy_n0 = src->dy_n0 > 0 ? src->dy_n0 : (1 << 30); v.dy_gap = src->dy_gap;
+  v.relu = src->relu; v.mode = src->mode;
+  v.cvalid = round_up(cin, 4);
   p.wp = (const uint8_t*)packed_w; p.bias = bias;
   p.y = dst->y; p.y_ct = dst->c_total; p.y_c0 = dst->c_off; p.y_n0 = dst->n0 > 0 ? dst->n0 : (1 << 30); p.y_gap = dst->gap;
   p.cout_valid = cout;

@@ -16,6 +16,7 @@
 // ring (producers: transform + bf16 hi/lo split; one thread issues the MMAs), then REDs its partial dW.
 #include "cvd_common.cuh"
 #include "tc_common.cuh"
+#include "fill.cuh"
 
 namespace {
 
@@ -23,10 +24,7 @@ constexpr int kThreads = 192;
 constexpr int kProducerThreads = 128;
 constexpr int TW = 16;                 // pixel-tile width = one K=16 step per tile row
 
-struct SrcView {
-  const float* x; const float* dy; const float* a; const float* b; const float4* bw;
-  int ct, c0, n0, gap, dy_ct, dy_c0, dy_n0, dy_gap, relu, mode, cvalid;
-};
+using fillns::SrcView;
 
 struct WgArgs {
   SrcView g, x;
@@ -42,71 +40,6 @@ struct WgArgs {
   int x_bytes, g_bytes, stage_bytes, nstages;
   int tmem_cols;
 };
-
-__device__ __forceinline__ int vphys(int c, int c0, int n0, int gap) { return c0 + c + (c >= n0 ? gap : 0); }
-
-// Stage a (rows x cols) window of one source tensor into chunk planes at `dst`.
-// Window pixel (r, c) is image pixel (y0 + r, x0 + c); out-of-image pixels are zero.
-__device__ __forceinline__ void fill_planes(const SrcView& s, uint8_t* dst, int plane_bytes, int nchunks, int lo_off,
-                                            int nsplit, int n, int H, int W, int y0, int x0, int rows, int cols, int tid)
-{
-  const int total = rows * cols * nchunks;
-  const size_t img_off = (size_t)n * H * W;
-  for (int it = tid; it < total; it += kProducerThreads) {
-    const int c8 = it % nchunks;
-    const int hp = it / nchunks;
-    const int r = hp / cols, c = hp - r * cols;
-    const int iy = y0 + r, ix = x0 + c;
-    const int cl = c8 * 8;
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.f;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W && cl < s.cvalid) {
-      const size_t pix = img_off + (size_t)iy * W + ix;
-      const int pc = vphys(cl, s.c0, s.n0, s.gap);
-      const float* xp = s.x + pix * s.ct + pc;
-      const bool second = cl + 4 < s.cvalid;
-      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 x0v = __ldg(reinterpret_cast<const float4*>(xp));
-      float4 x1v = second ? __ldg(reinterpret_cast<const float4*>(xp + 4)) : z4;
-      float xv[8] = {x0v.x, x0v.y, x0v.z, x0v.w, x1v.x, x1v.y, x1v.z, x1v.w};
-      if (s.a) {
-        float4 a0 = __ldg(reinterpret_cast<const float4*>(s.a + pc)), a1 = second ? __ldg(reinterpret_cast<const float4*>(s.a + pc + 4)) : z4;
-        float4 b0 = __ldg(reinterpret_cast<const float4*>(s.b + pc)), b1 = second ? __ldg(reinterpret_cast<const float4*>(s.b + pc + 4)) : z4;
-        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) xv[i] = fmaf(av[i], xv[i], bv[i]);
-      }
-      if (s.mode == CVD_XF_AFFINE) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = s.relu ? fmaxf(xv[i], 0.f) : xv[i];
-      } else {
-        const int dc = vphys(cl, s.dy_c0, s.dy_n0, s.dy_gap);
-        const float* dp = s.dy + pix * s.dy_ct + dc;
-        float4 d0 = __ldg(reinterpret_cast<const float4*>(dp));
-        float4 d1 = second ? __ldg(reinterpret_cast<const float4*>(dp + 4)) : z4;
-        const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (i >= 4 && !second) break;
-          const float4 cc = __ldg(s.bw + pc + i);
-          const float gq = (!s.relu || xv[i] > 0.f) ? dv[i] : 0.f;
-          v[i] = cc.x * gq - cc.y - cc.z * xv[i];
-        }
-      }
-      if (!second) {
-#pragma unroll
-        for (int i = 4; i < 8; ++i) v[i] = 0.f;
-      }
-    }
-    uint4 hi, lo;
-    tc::split8(v, hi, lo);
-    uint8_t* d = dst + (size_t)c8 * plane_bytes + (size_t)hp * 16;
-    *reinterpret_cast<uint4*>(d) = hi;
-    if (nsplit == 3) *reinterpret_cast<uint4*>(d + lo_off) = lo;
-  }
-}
 
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const WgArgs p)
@@ -124,7 +57,7 @@ wgrad_tc_kernel(const WgArgs p)
   const int taps = p.k * p.k;
   const int t0 = group * p.taps_per_group;
   const int t1 = min(taps, t0 + p.taps_per_group);
-  const int ky0 = t0 / p.k, ky1 = (t1 - 1) / p.k;
+  const int ky0 = t0 / p.k;
   // this CTA's tiles: slab, slab + nslabs, ...
   const int my_tiles = (p.ntiles - slab + p.nslabs - 1) / p.nslabs;
 
@@ -141,40 +74,48 @@ wgrad_tc_kernel(const WgArgs p)
   const int x_lo = p.x_chunks * p.x_plane, g_lo = p.g_chunks * p.g_plane;
 
   if (warp == 0) {
-    if (lane == 0 && my_tiles > 0) {
-      const uint32_t idesc = tc::idesc_bf16(p.Mrows, p.Ncols, 1, 1);   // both operands MN-major
-      const uint32_t sbase = tc::smem_u32(stages);
-      for (int it = 0; it < my_tiles; ++it) {
-        const int st = it % p.nstages;
-        tc::mbar_wait(&full[st], (uint32_t)((it / p.nstages) & 1));
-        tc::tc_fence_after();
-        const uint32_t xs = sbase + (uint32_t)st * p.stage_bytes;
-        const uint32_t gs = xs + (uint32_t)p.x_bytes;
+    // MMA issuer: uniform loop nest over the whole warp, one elected lane issues
+    const uint32_t idesc = tc::idesc_bf16(p.Mrows, p.Ncols, 1, 1);   // both operands MN-major
+    const uint32_t sbase = tc::smem_u32(stages);
+    const bool split = p.nsplit == 3;
+    const uint32_t m_plane = p.x_is_m ? p.x_plane : p.g_plane, n_plane = p.x_is_m ? p.g_plane : p.x_plane;
+    const uint32_t m_lo = p.x_is_m ? x_lo : g_lo, n_lo = p.x_is_m ? g_lo : x_lo;
+    const uint64_t mdesc0 = tc::smem_desc_base(128, m_plane), ndesc0 = tc::smem_desc_base(128, n_plane);
+    const uint32_t mb_stride = (uint32_t)(p.Mrows / 8) * m_plane;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int st = it % p.nstages;
+      tc::mbar_wait(&full[st], (uint32_t)((it / p.nstages) & 1));
+      tc::tc_fence_after();
+      const uint32_t xs = sbase + (uint32_t)st * p.stage_bytes;
+      const uint32_t gs = xs + (uint32_t)p.x_bytes;
+      if (tc::elect_one()) {
         for (int tap = t0; tap < t1; ++tap) {
           const int ky = tap / p.k, kx = tap - ky * p.k;
-          for (int r = 0; r < p.TH; ++r) {
-            // X window pixel (r + ky - ky0, kx + c), G pixel (r, c), c = 0..15
-            const uint32_t xa = xs + (uint32_t)(((r + ky - ky0) * p.xWP + kx) * 16);
-            const uint32_t ga = gs + (uint32_t)(r * TW * 16);
+          const uint32_t dtap = tmem_base + (uint32_t)((tap - t0) * p.mblk * p.Ncols);
+          // X window pixel (r + ky - ky0, kx + c), G pixel (r, c), c = 0..15
+          uint32_t xa = xs + (uint32_t)(((ky - ky0) * p.xWP + kx) * 16);
+          uint32_t ga = gs;
+          for (int r = 0; r < p.TH; ++r, xa += (uint32_t)p.xWP * 16, ga += TW * 16) {
+            const uint32_t acc = (it | r) ? 1u : 0u;
+            const uint32_t ma0 = p.x_is_m ? xa : ga, na = p.x_is_m ? ga : xa;
+            const uint64_t nd_hi = tc::smem_desc_at(ndesc0, na), nd_lo = tc::smem_desc_at(ndesc0, na + n_lo);
             for (int mb = 0; mb < p.mblk; ++mb) {
-              uint32_t ma, na, m_plane, n_plane, m_lo, n_lo;
-              if (p.x_is_m) { ma = xa + (uint32_t)(mb * (p.Mrows / 8) * p.x_plane); na = ga; m_plane = p.x_plane; n_plane = p.g_plane; m_lo = x_lo; n_lo = g_lo; }
-              else          { ma = ga + (uint32_t)(mb * (p.Mrows / 8) * p.g_plane); na = xa; m_plane = p.g_plane; n_plane = p.x_plane; m_lo = g_lo; n_lo = x_lo; }
-              const uint32_t d = tmem_base + (uint32_t)(((tap - t0) * p.mblk + mb) * p.Ncols);
-              const uint32_t acc = (it == 0 && r == 0) ? 0u : 1u;
-              const uint64_t md_hi = tc::smem_desc(ma, 128, m_plane), nd_hi = tc::smem_desc(na, 128, n_plane);
+              const uint32_t ma = ma0 + (uint32_t)mb * mb_stride;
+              const uint32_t d = dtap + (uint32_t)(mb * p.Ncols);
+              const uint64_t md_hi = tc::smem_desc_at(mdesc0, ma);
               tc::umma_f16(d, md_hi, nd_hi, idesc, acc);
-              if (p.nsplit == 3) {
-                tc::umma_f16(d, tc::smem_desc(ma + m_lo, 128, m_plane), nd_hi, idesc, 1u);
-                tc::umma_f16(d, md_hi, tc::smem_desc(na + n_lo, 128, n_plane), idesc, 1u);
+              if (split) {
+                tc::umma_f16(d, tc::smem_desc_at(mdesc0, ma + m_lo), nd_hi, idesc, 1u);
+                tc::umma_f16(d, md_hi, nd_lo, idesc, 1u);
               }
             }
           }
         }
         tc::umma_commit(&empty[st]);
       }
-      tc::umma_commit(acc_full);
+      __syncwarp();
     }
+    if (my_tiles > 0 && tc::elect_one()) tc::umma_commit(acc_full);
     __syncwarp();
   } else if (warp >= 2) {
     const int tid = threadIdx.x - 64;
@@ -187,8 +128,8 @@ wgrad_tc_kernel(const WgArgs p)
       const int oy = ty * p.TH, ox = tx * TW;
       uint8_t* xs = stages + (size_t)st * p.stage_bytes;
       uint8_t* gs = xs + p.x_bytes;
-      fill_planes(p.x, xs, p.x_plane, p.x_chunks, x_lo, p.nsplit, n, p.H, p.W, oy + ky0 - p.pad, ox - p.pad, p.xHP, p.xWP, tid);
-      fill_planes(p.g, gs, p.g_plane, p.g_chunks, g_lo, p.nsplit, n, p.H, p.W, oy, ox, p.TH, TW, tid);
+      fillns::fill_window(p.x, xs, p.x_plane, x_lo, p.nsplit, n, p.H, p.W, oy + ky0 - p.pad, ox - p.pad, p.xHP, p.xWP, 0, p.x_chunks, tid);
+      fillns::fill_window(p.g, gs, p.g_plane, g_lo, p.nsplit, n, p.H, p.W, oy, ox, p.TH, TW, 0, p.g_chunks, tid);
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&full[st]);
     }

@@ -13,6 +13,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// one lane of a fully converged warp (keeps the surrounding control flow warp-uniform, so descriptors and
+// loop counters stay in uniform registers instead of being re-broadcast per MMA)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -107,6 +115,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 //   K-major  operand: ((8 rows, n), 2 k-chunks) : ((16 B, SBO), LBO)   -> core matrix = 8 rows x 16 B contiguous
 //   MN-major operand: ((8 mn-elts=16 B, n), (8 k, kk)) : ((-, SBO), (16 B, LBO))
 // bits [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout type (0 = none)
+// descriptor with start address 0: add (byte_address >> 4) to the low word per MMA
+__device__ __forceinline__ uint64_t smem_desc_base(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ uint64_t smem_desc_at(uint64_t base, uint32_t saddr) { return base | (uint64_t)((saddr >> 4) & 0x3FFF); }
+
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);

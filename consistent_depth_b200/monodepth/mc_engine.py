@@ -103,7 +103,10 @@ class McParams:
             off += numel(s)
         self.n_flat = (off + 3) // 4 * 4
         self.flat = torch.zeros(self.n_flat, device=self.dev)
-        self.grad_flat = torch.zeros(self.n_flat, device=self.dev)
+        # flat gradient + one tail slot for the (local) loss: a single all-reduce carries both
+        self.grad_store = torch.zeros(self.n_flat + 4, device=self.dev)
+        self.grad_flat = self.grad_store[:self.n_flat]
+        self.loss_slot = self.grad_store[self.n_flat:self.n_flat + 1]
         self.bmap, boff = {}, 0
         for k, s in bufs:
             self.bmap[k] = (boff, s)
