@@ -49,13 +49,14 @@ struct ConvArgs {
   int mtx, mty, tiles_x, tiles_y;    // M-tiles per CTA along x / y
   int HP, WP, plane_bytes;           // halo dims, bytes of one 8-channel plane (padded)
   int slot_bytes, nslots, ngroups, gchunks;   // chunks (8 ch) per group
-  int stage_bytes, nstages;
+  int stage_bytes, nstages, kbs, kb_bytes;    // a weight stage = kbs k-blocks of kb_bytes each
   int tmem_cols;
 };
 
 __device__ __forceinline__ int view_phys(int c, int c0, int n0, int gap) { return c0 + c + (c >= n0 ? gap : 0); }
 
 // ------------------------------------------------------------------ the kernel
+template <int MT, int NSPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const ConvArgs p)
 {
@@ -95,50 +96,60 @@ conv_tc_kernel(const ConvArgs p)
   const uint32_t tmem_base = *tmem_base_sh;
 
   const int taps = p.k * p.k;
-  const int kb_total = taps * (p.cin >> 4);                      // number of weight stages streamed
+  const int stages_total = taps * (p.cin >> 4) / p.kbs;          // number of weight stages streamed
 
   if (warp == 0) {
     // ============================ MMA issuer ============================
     // The whole warp walks the (uniform) loop nest; one elected lane issues the tcgen05 instructions.
+    // MT (M-tiles per CTA) and the split are compile-time so the per-stage body is a straight run of
+    // UTCHMMAs with pre-computed descriptor offsets (the single issuing thread is the critical resource).
     const uint32_t idesc = tc::idesc_bf16(128, p.cout, 0, 0);
     const uint32_t a_base = tc::smem_u32(a_slots), b_base = tc::smem_u32(b_stages);
     const uint32_t lo_a = (uint32_t)p.gchunks * p.plane_bytes;      // hi -> lo plane offset inside a slot
-    const uint32_t lo_b = (uint32_t)p.cout * 32;                     // hi -> lo blob offset inside a stage
+    const uint32_t lo_b = (uint32_t)p.cout * 32;                     // hi -> lo blob offset inside a k-block
     const uint64_t adesc0 = tc::smem_desc_base((uint32_t)p.plane_bytes, (uint32_t)p.WP * 16);
     const uint64_t bdesc0 = tc::smem_desc_base(128, 256);
-    const bool split = p.nsplit == 3;
+    uint32_t aoff[MT], dcol[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int my = mt / p.mtx, mx = mt - my * p.mtx;
+      aoff[mt] = (uint32_t)((my * 16 * p.WP + mx * 8) * 16);
+      dcol[mt] = tmem_base + (uint32_t)(mt * p.cout);
+    }
     int stage = 0; uint32_t bphase = 0;
     for (int g = 0; g < p.ngroups; ++g) {
       const int slot = g % p.nslots;
       tc::mbar_wait(&a_full[slot], (uint32_t)((g / p.nslots) & 1));
       tc::tc_fence_after();
       const uint32_t slot_addr = a_base + (uint32_t)slot * p.slot_bytes;
-      const int kbg = min(kGroupCh, p.cin - g * kGroupCh) >> 4;      // 16-channel k-blocks in this group
+      const int nks = (min(kGroupCh, p.cin - g * kGroupCh) >> 4) / p.kbs;   // weight stages per tap in this group
+      uint32_t first = g ? 1u : 0u;
       for (int ky = 0; ky < p.k; ++ky) {
-        for (int kx = 0; kx < p.k; ++kx) {
-          for (int kb = 0; kb < kbg; ++kb) {
+        uint32_t a_row = slot_addr + (uint32_t)(ky * p.WP * 16);
+        for (int kx = 0; kx < p.k; ++kx, a_row += 16) {
+          for (int ks = 0; ks < nks; ++ks) {
             tc::mbar_wait(&b_full[stage], bphase);
             tc::tc_fence_after();
-            const uint32_t bs = b_base + (uint32_t)stage * p.stage_bytes;
-            const uint64_t bd_hi = tc::smem_desc_at(bdesc0, bs), bd_lo = tc::smem_desc_at(bdesc0, bs + lo_b);
-            const uint32_t acc0 = (g | ky | kx | kb) ? 1u : 0u;
-            const uint32_t a_tap = slot_addr + (uint32_t)(2 * kb) * p.plane_bytes + (uint32_t)((ky * p.WP + kx) * 16);
             if (tc::elect_one()) {
-              for (int my = 0; my < p.mty; ++my) {
-                for (int mx = 0; mx < p.mtx; ++mx) {
-                  const uint32_t a_addr = a_tap + (uint32_t)((my * 16 * p.WP + mx * 8) * 16);
-                  const uint32_t d = tmem_base + (uint32_t)((my * p.mtx + mx) * p.cout);
-                  const uint64_t ad_hi = tc::smem_desc_at(adesc0, a_addr);
-                  tc::umma_f16(d, ad_hi, bd_hi, idesc, acc0);
-                  if (split) {
-                    tc::umma_f16(d, tc::smem_desc_at(adesc0, a_addr + lo_a), bd_hi, idesc, 1u);
-                    tc::umma_f16(d, ad_hi, bd_lo, idesc, 1u);
+              uint32_t bs = b_base + (uint32_t)stage * p.stage_bytes;
+              uint32_t a_kb = a_row + (uint32_t)(2 * ks * p.kbs) * p.plane_bytes;
+              for (int j = 0; j < p.kbs; ++j, bs += p.kb_bytes, a_kb += 2 * p.plane_bytes) {
+                const uint64_t bd_hi = tc::smem_desc_at(bdesc0, bs), bd_lo = tc::smem_desc_at(bdesc0, bs + lo_b);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                  const uint64_t ad_hi = tc::smem_desc_at(adesc0, a_kb + aoff[mt]);
+                  tc::umma_f16(dcol[mt], ad_hi, bd_hi, idesc, first);
+                  if (NSPLIT == 3) {
+                    tc::umma_f16(dcol[mt], tc::smem_desc_at(adesc0, a_kb + aoff[mt] + lo_a), bd_hi, idesc, 1u);
+                    tc::umma_f16(dcol[mt], ad_hi, bd_lo, idesc, 1u);
                   }
                 }
+                first = 1u;
               }
               tc::umma_commit(&b_empty[stage]);        // weight stage reusable once these MMAs retire
             }
             __syncwarp();
+            first = 1u;
             if (++stage == p.nstages) { stage = 0; bphase ^= 1; }
           }
         }
@@ -153,7 +164,7 @@ conv_tc_kernel(const ConvArgs p)
     if (lane == 0) {
       int stage = 0; uint32_t ephase = 0;
       const uint8_t* src = p.wp;
-      for (int i = 0; i < kb_total; ++i) {
+      for (int i = 0; i < stages_total; ++i) {
         if (i >= p.nstages) tc::mbar_wait(&b_empty[stage], ephase);
         tc::mbar_arrive_expect_tx(&b_full[stage], (uint32_t)p.stage_bytes);
         tc::bulk_g2s(b_stages + (size_t)stage * p.stage_bytes, src, (uint32_t)p.stage_bytes, &b_full[stage]);
@@ -311,7 +322,14 @@ extern "C" int cvd_conv_fwd(const cvd_src_t* src, const void* packed_w, const fl
   p.flags = flags; p.nsplit = precision;
   p.ngroups = (p.cin + kGroupCh - 1) / kGroupCh;
   p.gchunks = (p.ngroups == 1 ? p.cin : kGroupCh) / 8;
-  p.stage_bytes = p.cout * 32 * (precision == 3 ? 2 : 1);
+  p.kb_bytes = p.cout * 32 * (precision == 3 ? 2 : 1);
+  {   // k-blocks per weight stage: divides every group's k-block count, stage <= 16 KB
+    const int last_kb = ((p.cin - (p.ngroups - 1) * kGroupCh) >> 4);
+    int kbs = 4;
+    while (kbs > 1 && (last_kb % kbs != 0 || ((p.ngroups > 1 ? kGroupCh : p.cin) >> 4) % kbs != 0 || kbs * p.kb_bytes > 16384)) kbs >>= 1;
+    p.kbs = kbs;
+  }
+  p.stage_bytes = p.kbs * p.kb_bytes;
 
   // choose the CTA tile: as many 8x16 M-tiles as TMEM (512 cols) and shared memory allow
   const int smem_budget = 200 * 1024;
@@ -339,8 +357,8 @@ extern "C" int cvd_conv_fwd(const cvd_src_t* src, const void* packed_w, const fl
   }
   CVD_CHECK_ARG(best_mtx > 0, "cvd_conv_fwd: no tile fits shared memory (cin=%d cout=%d k=%d)", cin, cout, k);
   p.mtx = best_mtx; p.mty = best_mty; p.nslots = best_nslots; p.nstages = best_nst;
-  const int kb_total = k * k * (p.cin >> 4);
-  if (p.nstages > kb_total) p.nstages = kb_total < 1 ? 1 : kb_total;
+  const int stages_total = k * k * (p.cin >> 4) / p.kbs;
+  if (p.nstages > stages_total) p.nstages = stages_total < 1 ? 1 : stages_total;
   p.tiles_x = (W + 8 * p.mtx - 1) / (8 * p.mtx);
   p.tiles_y = (H + 16 * p.mty - 1) / (16 * p.mty);
   int cols = p.mtx * p.mty * p.cout, pw = 32;
@@ -349,15 +367,26 @@ extern "C" int cvd_conv_fwd(const cvd_src_t* src, const void* packed_w, const fl
   CVD_CHECK_ARG(p.plane_bytes < (1 << 18) && p.WP * 16 < (1 << 18), "cvd_conv_fwd: descriptor offset overflow");
 
   const size_t smem = (size_t)p.nslots * p.slot_bytes + (size_t)p.nstages * p.stage_bytes + 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-    if (e != cudaSuccess) return cvd_fail("cvd_conv_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = 227 * 1024;
-  }
   const long long grid = (long long)N * p.tiles_x * p.tiles_y;
   CVD_CHECK_ARG(grid < (1ll << 31), "cvd_conv_fwd: grid too large");
-  conv_tc_kernel<<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+  const int MT = p.mtx * p.mty;
+  cudaError_t e = cudaSuccess;
+#define CVD_CONV_LAUNCH(MTV, NS)                                                                             \
+  do {                                                                                                       \
+    static bool cfg = false;                                                                                 \
+    if (!cfg) {                                                                                              \
+      e = cudaFuncSetAttribute(conv_tc_kernel<MTV, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)); \
+      cfg = true;                                                                                            \
+    }                                                                                                        \
+    if (e == cudaSuccess) conv_tc_kernel<MTV, NS><<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(p); \
+  } while (0)
+#define CVD_CONV_MT(NS)                                                                                      \
+  do {                                                                                                       \
+    if (MT == 8) CVD_CONV_LAUNCH(8, NS); else if (MT == 4) CVD_CONV_LAUNCH(4, NS);                           \
+    else if (MT == 2) CVD_CONV_LAUNCH(2, NS); else CVD_CONV_LAUNCH(1, NS);                                   \
+  } while (0)
+  if (precision == 3) CVD_CONV_MT(3); else CVD_CONV_MT(1);
+  if (e != cudaSuccess) return cvd_fail("cvd_conv_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   CVD_LAUNCH_OK("conv_tc_kernel");
   return 0;
 }

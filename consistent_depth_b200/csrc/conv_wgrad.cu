@@ -41,6 +41,7 @@ struct WgArgs {
   int tmem_cols;
 };
 
+template <int MBLK, int NSPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const WgArgs p)
 {
@@ -77,7 +78,6 @@ wgrad_tc_kernel(const WgArgs p)
     // MMA issuer: uniform loop nest over the whole warp, one elected lane issues
     const uint32_t idesc = tc::idesc_bf16(p.Mrows, p.Ncols, 1, 1);   // both operands MN-major
     const uint32_t sbase = tc::smem_u32(stages);
-    const bool split = p.nsplit == 3;
     const uint32_t m_plane = p.x_is_m ? p.x_plane : p.g_plane, n_plane = p.x_is_m ? p.g_plane : p.x_plane;
     const uint32_t m_lo = p.x_is_m ? x_lo : g_lo, n_lo = p.x_is_m ? g_lo : x_lo;
     const uint64_t mdesc0 = tc::smem_desc_base(128, m_plane), ndesc0 = tc::smem_desc_base(128, n_plane);
@@ -89,27 +89,33 @@ wgrad_tc_kernel(const WgArgs p)
       const uint32_t xs = sbase + (uint32_t)st * p.stage_bytes;
       const uint32_t gs = xs + (uint32_t)p.x_bytes;
       if (tc::elect_one()) {
+        // taps t0..t1-1 in raster order without divisions; per tap a straight run of TH x MBLK x NSPLIT MMAs
+        int ky = ky0, kx = t0 - ky0 * p.k;
+        uint32_t dtap = tmem_base;
+        const uint32_t x_row = (uint32_t)p.xWP * 16;
         for (int tap = t0; tap < t1; ++tap) {
-          const int ky = tap / p.k, kx = tap - ky * p.k;
-          const uint32_t dtap = tmem_base + (uint32_t)((tap - t0) * p.mblk * p.Ncols);
           // X window pixel (r + ky - ky0, kx + c), G pixel (r, c), c = 0..15
           uint32_t xa = xs + (uint32_t)(((ky - ky0) * p.xWP + kx) * 16);
           uint32_t ga = gs;
-          for (int r = 0; r < p.TH; ++r, xa += (uint32_t)p.xWP * 16, ga += TW * 16) {
-            const uint32_t acc = (it | r) ? 1u : 0u;
+          uint32_t acc = it ? 1u : 0u;
+          for (int r = 0; r < p.TH; ++r, xa += x_row, ga += TW * 16) {
             const uint32_t ma0 = p.x_is_m ? xa : ga, na = p.x_is_m ? ga : xa;
             const uint64_t nd_hi = tc::smem_desc_at(ndesc0, na), nd_lo = tc::smem_desc_at(ndesc0, na + n_lo);
-            for (int mb = 0; mb < p.mblk; ++mb) {
+#pragma unroll
+            for (int mb = 0; mb < MBLK; ++mb) {
               const uint32_t ma = ma0 + (uint32_t)mb * mb_stride;
               const uint32_t d = dtap + (uint32_t)(mb * p.Ncols);
               const uint64_t md_hi = tc::smem_desc_at(mdesc0, ma);
               tc::umma_f16(d, md_hi, nd_hi, idesc, acc);
-              if (split) {
+              if (NSPLIT == 3) {
                 tc::umma_f16(d, tc::smem_desc_at(mdesc0, ma + m_lo), nd_hi, idesc, 1u);
                 tc::umma_f16(d, md_hi, nd_lo, idesc, 1u);
               }
             }
+            acc = 1u;
           }
+          dtap += (uint32_t)(MBLK * p.Ncols);
+          if (++kx == p.k) { kx = 0; ++ky; }
         }
         tc::umma_commit(&empty[st]);
       }
@@ -196,7 +202,7 @@ extern "C" int cvd_conv_wgrad(const cvd_src_t* gsrc, const cvd_src_t* xsrc, floa
   p.Mrows = cm <= 64 ? 64 : 128;
   p.mblk = (cm + p.Mrows - 1) / p.Mrows;
   p.Ncols = cn;
-  CVD_CHECK_ARG(p.mblk * p.Ncols <= 512, "cvd_conv_wgrad: accumulator does not fit TMEM");
+  CVD_CHECK_ARG(p.mblk * p.Ncols <= 512 && p.mblk <= 2, "cvd_conv_wgrad: accumulator does not fit TMEM");
   const int taps = k * k;
   p.taps_per_group = 512 / (p.mblk * p.Ncols);
   if (p.taps_per_group > taps) p.taps_per_group = taps;
@@ -232,13 +238,19 @@ extern "C" int cvd_conv_wgrad(const cvd_src_t* gsrc, const cvd_src_t* xsrc, floa
   while (pw < cols) pw <<= 1;
   p.tmem_cols = pw;
   const size_t smem = (size_t)p.nstages * p.stage_bytes + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-    if (e != cudaSuccess) return cvd_fail("cvd_conv_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
-  }
-  wgrad_tc_kernel<<<dim3(p.nslabs, p.ngroups), kThreads, smem, (cudaStream_t)stream>>>(p);
+  cudaError_t e = cudaSuccess;
+#define CVD_WG_LAUNCH(MB, NS)                                                                                 \
+  do {                                                                                                        \
+    static bool cfg = false;                                                                                  \
+    if (!cfg) {                                                                                               \
+      e = cudaFuncSetAttribute(wgrad_tc_kernel<MB, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)); \
+      cfg = true;                                                                                             \
+    }                                                                                                         \
+    if (e == cudaSuccess) wgrad_tc_kernel<MB, NS><<<dim3(p.nslabs, p.ngroups), kThreads, smem, (cudaStream_t)stream>>>(p); \
+  } while (0)
+  if (p.mblk == 1) { if (precision == 3) CVD_WG_LAUNCH(1, 3); else CVD_WG_LAUNCH(1, 1); }
+  else             { if (precision == 3) CVD_WG_LAUNCH(2, 3); else CVD_WG_LAUNCH(2, 1); }
+  if (e != cudaSuccess) return cvd_fail("cvd_conv_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   CVD_LAUNCH_OK("wgrad_tc_kernel");
   return 0;
 }
