@@ -21,17 +21,21 @@
 // Precision: bf16 tensor cores with the operands split v = hi + lo (3 MMAs: hi*hi, lo*hi, hi*lo,
 // fp32 accumulate in TMEM) => fp32-class results ("precision 3"), or plain bf16 ("precision 1").
 //
-// Warp roles (192 threads): warp 0 = TMEM allocator + single-thread MMA issuer; warp 1 = weight
-// streamer (cp.async.bulk of pre-packed core-matrix blobs through an mbarrier ring); warps 2-5 =
-// activation producers (global -> transform -> bf16 hi/lo -> smem), then epilogue
-// (tcgen05.ld -> +bias / exp -> NHWC global stores).
+// Persistent, warp-specialised pipeline (one CTA per SM, 320 threads, each CTA loops over output tiles):
+//   warp 0      TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma / commit)
+//   warp 1      weight streamer: cp.async.bulk of pre-packed core-matrix blobs through an mbarrier ring
+//   warps 2-5   activation producers: global -> transform -> bf16 hi/lo -> smem slot (ring of 1-2 slots)
+//   warps 6-9   epilogue: tcgen05.ld -> +bias / exp -> NHWC global stores
+// Two TMEM accumulator buffers and the slot ring let tile t's epilogue, tile t+1's MMAs and tile t+2's
+// activation staging run concurrently; for large filters the 64 input channels are staged as two
+// 32-channel slots so staging overlaps the MMAs even when one full-depth halo tile is all that fits.
 #include "cvd_common.cuh"
 #include "tc_common.cuh"
 #include "fill.cuh"
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;
 constexpr int kProducerThreads = 128;
 constexpr int kMaxStages = 8;
 constexpr int kGroupCh = 64;          // channels per activation group resident in one A slot
@@ -48,7 +52,9 @@ struct ConvArgs {
   // tiling
   int mtx, mty, tiles_x, tiles_y;    // M-tiles per CTA along x / y
   int HP, WP, plane_bytes;           // halo dims, bytes of one 8-channel plane (padded)
-  int slot_bytes, nslots, ngroups, gchunks;   // chunks (8 ch) per group
+  int slot_bytes, nslots, ngroups, gchunks;   // items per tile, chunks (8 ch) per item (max)
+  int gsplit;                                 // 1: an item = one 64-channel pack group; 2: half of it (32 ch)
+  int ntiles;
   int stage_bytes, nstages, kbs, kb_bytes;    // a weight stage = kbs k-blocks of kb_bytes each
   int tmem_cols;
 };
@@ -69,21 +75,18 @@ conv_tc_kernel(const ConvArgs p)
   uint64_t* b_empty = bars + kMaxStages;         // [kMaxStages]
   uint64_t* a_full = bars + 2 * kMaxStages;      // [2]
   uint64_t* a_empty = a_full + 2;                // [2]
-  uint64_t* acc_full = a_empty + 2;              // [1]
-  uint32_t* tmem_base_sh = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_full = a_empty + 2;              // [2]
+  uint64_t* acc_empty = acc_full + 2;            // [2]
+  uint32_t* tmem_base_sh = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // tile coordinates
-  int t = blockIdx.x;
-  const int tx = t % p.tiles_x; t /= p.tiles_x;
-  const int ty = t % p.tiles_y; const int n = t / p.tiles_y;
-  const int ox = tx * (8 * p.mtx), oy = ty * (16 * p.mty);
-
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.nstages; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&a_full[i], kProducerThreads); tc::mbar_init(&a_empty[i], 1); }
-    tc::mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&a_full[i], kProducerThreads); tc::mbar_init(&a_empty[i], 1);
+      tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 4);
+    }
     tc::mbar_fence_init();
   }
   if (warp == 0) {
@@ -96,108 +99,142 @@ conv_tc_kernel(const ConvArgs p)
   const uint32_t tmem_base = *tmem_base_sh;
 
   const int taps = p.k * p.k;
-  const int stages_total = taps * (p.cin >> 4) / p.kbs;          // number of weight stages streamed
+  const int kb_full = (p.ngroups == 1 ? p.cin : kGroupCh * 1) >> 4;   // placeholder, recomputed per item below
+
+  // item i of a tile -> (pack group g64, sub-group h): channel range and k-block range inside the pack group
+  auto item_cfirst = [&](int it) { return p.gsplit == 2 ? (it >> 1) * kGroupCh + (it & 1) * 32 : it * kGroupCh; };
+  auto item_chunks = [&](int it) { return p.gsplit == 2 ? 4 : min(p.gchunks, (p.cin - it * kGroupCh) >> 3); };
+  (void)kb_full;
 
   if (warp == 0) {
     // ============================ MMA issuer ============================
-    // The whole warp walks the (uniform) loop nest; one elected lane issues the tcgen05 instructions.
-    // MT (M-tiles per CTA) and the split are compile-time so the per-stage body is a straight run of
-    // UTCHMMAs with pre-computed descriptor offsets (the single issuing thread is the critical resource).
     const uint32_t idesc = tc::idesc_bf16(128, p.cout, 0, 0);
     const uint32_t a_base = tc::smem_u32(a_slots), b_base = tc::smem_u32(b_stages);
     const uint32_t lo_a = (uint32_t)p.gchunks * p.plane_bytes;      // hi -> lo plane offset inside a slot
     const uint32_t lo_b = (uint32_t)p.cout * 32;                     // hi -> lo blob offset inside a k-block
     const uint64_t adesc0 = tc::smem_desc_base((uint32_t)p.plane_bytes, (uint32_t)p.WP * 16);
     const uint64_t bdesc0 = tc::smem_desc_base(128, 256);
-    uint32_t aoff[MT], dcol[MT];
+    uint32_t aoff[MT];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
       const int my = mt / p.mtx, mx = mt - my * p.mtx;
       aoff[mt] = (uint32_t)((my * 16 * p.WP + mx * 8) * 16);
-      dcol[mt] = tmem_base + (uint32_t)(mt * p.cout);
     }
     int stage = 0; uint32_t bphase = 0;
-    for (int g = 0; g < p.ngroups; ++g) {
-      const int slot = g % p.nslots;
-      tc::mbar_wait(&a_full[slot], (uint32_t)((g / p.nslots) & 1));
-      tc::tc_fence_after();
-      const uint32_t slot_addr = a_base + (uint32_t)slot * p.slot_bytes;
-      const int nks = (min(kGroupCh, p.cin - g * kGroupCh) >> 4) / p.kbs;   // weight stages per tap in this group
-      uint32_t first = g ? 1u : 0u;
-      for (int ky = 0; ky < p.k; ++ky) {
-        uint32_t a_row = slot_addr + (uint32_t)(ky * p.WP * 16);
-        for (int kx = 0; kx < p.k; ++kx, a_row += 16) {
-          for (int ks = 0; ks < nks; ++ks) {
-            tc::mbar_wait(&b_full[stage], bphase);
-            tc::tc_fence_after();
-            if (tc::elect_one()) {
-              uint32_t bs = b_base + (uint32_t)stage * p.stage_bytes;
-              uint32_t a_kb = a_row + (uint32_t)(2 * ks * p.kbs) * p.plane_bytes;
-              for (int j = 0; j < p.kbs; ++j, bs += p.kb_bytes, a_kb += 2 * p.plane_bytes) {
-                const uint64_t bd_hi = tc::smem_desc_at(bdesc0, bs), bd_lo = tc::smem_desc_at(bdesc0, bs + lo_b);
+    int item = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
+      const int buf = ti & 1;
+      if (ti >= 2) { tc::mbar_wait(&acc_empty[buf], (uint32_t)(((ti >> 1) - 1) & 1)); tc::tc_fence_after(); }
+      const uint32_t dbase = tmem_base + (uint32_t)(buf * MT * p.cout);
+      uint32_t first = 0u;
+      for (int g = 0; g < p.ngroups; ++g, ++item) {
+        const int slot = item % p.nslots;
+        tc::mbar_wait(&a_full[slot], (uint32_t)((item / p.nslots) & 1));
+        tc::tc_fence_after();
+        const uint32_t slot_addr = a_base + (uint32_t)slot * p.slot_bytes;
+        const int nks = (item_chunks(g) >> 1) / p.kbs;              // weight stages per tap for this item
+        for (int ky = 0; ky < p.k; ++ky) {
+          uint32_t a_row = slot_addr + (uint32_t)(ky * p.WP * 16);
+          for (int kx = 0; kx < p.k; ++kx, a_row += 16) {
+            for (int ks = 0; ks < nks; ++ks) {
+              tc::mbar_wait(&b_full[stage], bphase);
+              tc::tc_fence_after();
+              if (tc::elect_one()) {
+                uint32_t bs = b_base + (uint32_t)stage * p.stage_bytes;
+                uint32_t a_kb = a_row + (uint32_t)(2 * ks * p.kbs) * p.plane_bytes;
+                for (int j = 0; j < p.kbs; ++j, bs += p.kb_bytes, a_kb += 2 * p.plane_bytes) {
+                  const uint64_t bd_hi = tc::smem_desc_at(bdesc0, bs), bd_lo = tc::smem_desc_at(bdesc0, bs + lo_b);
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                  const uint64_t ad_hi = tc::smem_desc_at(adesc0, a_kb + aoff[mt]);
-                  tc::umma_f16(dcol[mt], ad_hi, bd_hi, idesc, first);
-                  if (NSPLIT == 3) {
-                    tc::umma_f16(dcol[mt], tc::smem_desc_at(adesc0, a_kb + aoff[mt] + lo_a), bd_hi, idesc, 1u);
-                    tc::umma_f16(dcol[mt], ad_hi, bd_lo, idesc, 1u);
+                  for (int mt = 0; mt < MT; ++mt) {
+                    const uint32_t d = dbase + (uint32_t)(mt * p.cout);
+                    const uint64_t ad_hi = tc::smem_desc_at(adesc0, a_kb + aoff[mt]);
+                    tc::umma_f16(d, ad_hi, bd_hi, idesc, first);
+                    if (NSPLIT == 3) {
+                      tc::umma_f16(d, tc::smem_desc_at(adesc0, a_kb + aoff[mt] + lo_a), bd_hi, idesc, 1u);
+                      tc::umma_f16(d, ad_hi, bd_lo, idesc, 1u);
+                    }
                   }
+                  first = 1u;
                 }
-                first = 1u;
+                tc::umma_commit(&b_empty[stage]);        // weight stage reusable once these MMAs retire
               }
-              tc::umma_commit(&b_empty[stage]);        // weight stage reusable once these MMAs retire
+              __syncwarp();
+              first = 1u;
+              if (++stage == p.nstages) { stage = 0; bphase ^= 1; }
             }
-            __syncwarp();
-            first = 1u;
-            if (++stage == p.nstages) { stage = 0; bphase ^= 1; }
           }
         }
+        if (tc::elect_one()) tc::umma_commit(&a_empty[slot]);   // activation slot reusable
+        __syncwarp();
       }
-      if (tc::elect_one()) tc::umma_commit(&a_empty[slot]);   // activation slot reusable
+      if (tc::elect_one()) tc::umma_commit(&acc_full[buf]);     // this tile's accumulators complete
       __syncwarp();
     }
-    if (tc::elect_one()) tc::umma_commit(acc_full);           // accumulators complete
-    __syncwarp();
   } else if (warp == 1) {
     // ============================ weight streamer ============================
     if (lane == 0) {
-      int stage = 0; uint32_t ephase = 0;
-      const uint8_t* src = p.wp;
-      for (int i = 0; i < stages_total; ++i) {
-        if (i >= p.nstages) tc::mbar_wait(&b_empty[stage], ephase);
-        tc::mbar_arrive_expect_tx(&b_full[stage], (uint32_t)p.stage_bytes);
-        tc::bulk_g2s(b_stages + (size_t)stage * p.stage_bytes, src, (uint32_t)p.stage_bytes, &b_full[stage]);
-        src += p.stage_bytes;
-        if (++stage == p.nstages) { stage = 0; if (i >= p.nstages) ephase ^= 1; }
+      int stage = 0; uint32_t ephase = 0; long long issued = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        for (int g = 0; g < p.ngroups; ++g) {
+          const int g64 = p.gsplit == 2 ? (g >> 1) : g;
+          const int kbg = min(kGroupCh, p.cin - g64 * kGroupCh) >> 4;       // k-blocks of the pack group
+          const int kb0 = p.gsplit == 2 ? (g & 1) * 2 : 0;                  // first k-block of this item
+          const int nks = (item_chunks(g) >> 1) / p.kbs;
+          const uint8_t* gsrc = p.wp + (size_t)g64 * taps * (kGroupCh / 16) * p.kb_bytes;
+          for (int tap = 0; tap < taps; ++tap) {
+            for (int ks = 0; ks < nks; ++ks, ++issued) {
+              if (issued >= p.nstages) {
+                tc::mbar_wait(&b_empty[stage], ephase);
+              }
+              const uint8_t* src = gsrc + (size_t)(tap * kbg + kb0 + ks * p.kbs) * p.kb_bytes;
+              tc::mbar_arrive_expect_tx(&b_full[stage], (uint32_t)p.stage_bytes);
+              tc::bulk_g2s(b_stages + (size_t)stage * p.stage_bytes, src, (uint32_t)p.stage_bytes, &b_full[stage]);
+              if (++stage == p.nstages) { stage = 0; if (issued >= p.nstages) ephase ^= 1; }
+            }
+          }
+        }
       }
     }
     __syncwarp();
-  } else {
-    // ============================ activation producers, then epilogue ============================
+  } else if (warp < 6) {
+    // ============================ activation producers ============================
     const int tid = threadIdx.x - 64;
-    for (int g = 0; g < p.ngroups; ++g) {
-      const int slot = g % p.nslots;
-      if (g >= p.nslots) tc::mbar_wait(&a_empty[slot], (uint32_t)(((g / p.nslots) - 1) & 1));
-      fillns::fill_window(p.src, a_slots + (size_t)slot * p.slot_bytes, p.plane_bytes, p.gchunks * p.plane_bytes, p.nsplit,
-                          n, p.H, p.W, oy - p.pad, ox - p.pad, p.HP, p.WP, g * kGroupCh,
-                          min(p.gchunks, (p.cin - g * kGroupCh) >> 3), tid);
-      tc::fence_proxy_async_smem();
-      tc::mbar_arrive(&a_full[slot]);
+    int item = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      int t = tile;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; const int n = t / p.tiles_y;
+      const int ox = tx * (8 * p.mtx), oy = ty * (16 * p.mty);
+      for (int g = 0; g < p.ngroups; ++g, ++item) {
+        const int slot = item % p.nslots;
+        if (item >= p.nslots) tc::mbar_wait(&a_empty[slot], (uint32_t)(((item / p.nslots) - 1) & 1));
+        fillns::fill_window(p.src, a_slots + (size_t)slot * p.slot_bytes, p.plane_bytes, p.gchunks * p.plane_bytes, p.nsplit,
+                            n, p.H, p.W, oy - p.pad, ox - p.pad, p.HP, p.WP, item_cfirst(g), item_chunks(g), tid);
+        tc::fence_proxy_async_smem();
+        tc::mbar_arrive(&a_full[slot]);
+      }
     }
-
-    tc::mbar_wait(acc_full, 0);
-    tc::tc_fence_after();
+  } else {
+    // ============================ epilogue ============================
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;                   // accumulator row = pixel inside the M-tile
     const int py = row >> 3, px = row & 7;
     const bool accum = (p.flags & 1) != 0, do_exp = (p.flags & 2) != 0;
-    for (int my = 0; my < p.mty; ++my) {
-      for (int mx = 0; mx < p.mtx; ++mx) {
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
+      int t = tile;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; const int n = t / p.tiles_y;
+      const int ox = tx * (8 * p.mtx), oy = ty * (16 * p.mty);
+      const int buf = ti & 1;
+      tc::mbar_wait(&acc_full[buf], (uint32_t)((ti >> 1) & 1));
+      tc::tc_fence_after();
+      for (int mt = 0; mt < MT; ++mt) {
+        const int my = mt / p.mtx, mx = mt - my * p.mtx;
         const int yy = oy + my * 16 + py, xx = ox + mx * 8 + px;
         const bool inside = yy < p.H && xx < p.W;
         float* yp = p.y + (((size_t)n * p.H + (inside ? yy : 0)) * p.W + (inside ? xx : 0)) * p.y_ct;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((my * p.mtx + mx) * p.cout);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * MT + mt) * p.cout);
         for (int c16 = 0; c16 < p.cout; c16 += 16) {
           float v[16];
           tc::tmem_ld16(taddr + (uint32_t)c16, v);    // warp-collective: executed by all lanes
@@ -223,6 +260,9 @@ conv_tc_kernel(const ConvArgs p)
           }
         }
       }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);   // accumulator buffer free for tile ti + 2
     }
   }
 
@@ -235,14 +275,15 @@ conv_tc_kernel(const ConvArgs p)
 // fp32 OIHW -> per (group, tap, k-block) blobs [hi: cout x 16 ch][lo: cout x 16 ch], each in the
 // UMMA SWIZZLE_NONE K-major core-matrix order: blob[n/8][kk/8][n%8][kk%8] (LBO = 128 B, SBO = 256 B).
 // transpose_flip builds the dgrad operand: W'[ci][co][k-1-ky][k-1-kx].
-__global__ void pack_weights_kernel(const float* __restrict__ w, int cin_w, int cout_w, int k, int transpose_flip,
-                                    int cin_pad, int cout_pad, int nsplit, uint8_t* __restrict__ out)
+__device__ __forceinline__ void pack_one(const float* __restrict__ w, int cin_w, int cout_w, int k, int transpose_flip,
+                                         int cin_pad, int cout_pad, int nsplit, uint8_t* __restrict__ out,
+                                         long long first, long long step)
 {
   // logical GEMM dims: K-channels = cin_pad (multiple of 16), N = cout_pad (multiple of 16)
   const int taps = k * k;
   const int stage_bytes = cout_pad * 32 * (nsplit == 3 ? 2 : 1);
   const long long total = (long long)cin_pad * cout_pad * taps;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  for (long long i = first; i < total; i += step) {
     const int c = (int)(i % cin_pad);
     const int nn = (int)((i / cin_pad) % cout_pad);
     const int tap = (int)(i / ((long long)cin_pad * cout_pad));
@@ -265,6 +306,24 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cin_w, int 
     *reinterpret_cast<__nv_bfloat16*>(out + off) = h;
     if (nsplit == 3) *reinterpret_cast<__nv_bfloat16*>(out + off + (size_t)cout_pad * 32) = __float2bfloat16_rn(v - __bfloat162float(h));
   }
+}
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, int cin_w, int cout_w, int k, int transpose_flip,
+                                    int cin_pad, int cout_pad, int nsplit, uint8_t* __restrict__ out)
+{
+  pack_one(w, cin_w, cout_w, k, transpose_flip, cin_pad, cout_pad, nsplit, out,
+           (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+
+struct PackDesc { const float* w; uint8_t* out; int cin, cout, k, flip; };
+
+// all convolutions of a network in ONE launch (blockIdx.y = conv): replaces ~180 tiny launches per step
+__global__ void pack_weights_batch_kernel(const PackDesc* __restrict__ descs, int nsplit)
+{
+  const PackDesc d = descs[blockIdx.y];
+  const int kc = d.flip ? d.cout : d.cin, nc = d.flip ? d.cin : d.cout;
+  pack_one(d.w, d.cin, d.cout, d.k, d.flip, (kc + 15) / 16 * 16, (nc + 15) / 16 * 16, nsplit, d.out,
+           (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
 }
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -290,6 +349,15 @@ extern "C" int cvd_conv_pack_weights(const float* w_oihw, int cin, int cout, int
   pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, cin, cout, k, transpose_flip,
                                                                           cin_pad, cout_pad, precision, (uint8_t*)packed);
   CVD_LAUNCH_OK("pack_weights_kernel");
+  return 0;
+}
+
+extern "C" int cvd_conv_pack_batch(const void* descs_dev, int n, int precision, void* stream)
+{
+  CVD_CHECK_ARG(descs_dev && n > 0, "cvd_conv_pack_batch: bad arguments");
+  CVD_CHECK_ARG(precision == 1 || precision == 3, "cvd_conv_pack_batch: precision must be 1 or 3");
+  pack_weights_batch_kernel<<<dim3(16, n), 256, 0, (cudaStream_t)stream>>>((const PackDesc*)descs_dev, precision);
+  CVD_LAUNCH_OK("pack_weights_batch_kernel");
   return 0;
 }
 
@@ -320,55 +388,61 @@ extern "C" int cvd_conv_fwd(const cvd_src_t* src, const void* packed_w, const fl
   p.cin = round_up(cin, 16); p.cout = round_up(cout, 16);
   CVD_CHECK_ARG(p.cout <= 256, "cvd_conv_fwd: cout=%d > 256", cout);
   p.flags = flags; p.nsplit = precision;
-  p.ngroups = (p.cin + kGroupCh - 1) / kGroupCh;
-  p.gchunks = (p.ngroups == 1 ? p.cin : kGroupCh) / 8;
+  const int ng64 = (p.cin + kGroupCh - 1) / kGroupCh;
   p.kb_bytes = p.cout * 32 * (precision == 3 ? 2 : 1);
-  {   // k-blocks per weight stage: divides every group's k-block count, stage <= 16 KB
-    const int last_kb = ((p.cin - (p.ngroups - 1) * kGroupCh) >> 4);
-    int kbs = 4;
-    while (kbs > 1 && (last_kb % kbs != 0 || ((p.ngroups > 1 ? kGroupCh : p.cin) >> 4) % kbs != 0 || kbs * p.kb_bytes > 16384)) kbs >>= 1;
-    p.kbs = kbs;
-  }
-  p.stage_bytes = p.kbs * p.kb_bytes;
 
-  // choose the CTA tile: as many 8x16 M-tiles as TMEM (512 cols) and shared memory allow
-  const int smem_budget = 200 * 1024;
-  int best_mtx = 0, best_mty = 0, best_nslots = 1, best_nst = 2;
+  // Choose the CTA tile (M-tiles of 8x16 px), the channels per staging slot (64, or 32 = "gsplit 2") and the
+  // number of slots.  Two TMEM accumulator buffers: 2 * MT * cout <= 512 columns.  Preference: two slots
+  // (staging overlaps the MMAs) with the largest tile that fits; else one slot.
+  const int smem_budget = 212 * 1024;
   const int cand[6][2] = {{4, 2}, {4, 1}, {2, 2}, {2, 1}, {1, 2}, {1, 1}};   // (mtx, mty), largest first
-  for (int ci = 0; ci < 6 && !best_mtx; ++ci) {
-    const int mtx = cand[ci][0], mty = cand[ci][1];
-    if (mtx * mty * p.cout > 512) continue;
-    if (8 * mtx > round_up(W, 8) && mtx > 1) continue;
-    if (16 * mty > round_up(H, 16) && mty > 1) continue;
-    const int HP = 16 * mty + k - 1, WP = 8 * mtx + k - 1;
-    int plane = HP * WP * 16;
-    // producer store bank spreading: plane stride = 16*q (mod 128) with q = pixels per quarter-warp
-    const int q = p.gchunks >= 8 ? 1 : 8 / p.gchunks;
-    plane = (plane + 127) / 128 * 128 + 16 * q;
-    const int slot = plane * p.gchunks * (precision == 3 ? 2 : 1);
-    const int nslots = p.ngroups > 1 ? 2 : 1;
-    for (int nst = kMaxStages; nst >= 2; --nst) {
-      if ((size_t)nslots * slot + (size_t)nst * p.stage_bytes + 1024 <= (size_t)smem_budget) {
-        best_mtx = mtx; best_mty = mty; best_nslots = nslots; best_nst = nst;
-        p.HP = HP; p.WP = WP; p.plane_bytes = plane; p.slot_bytes = slot;
-        break;
+  bool found = false;
+  for (int want_slots = 2; want_slots >= 1 && !found; --want_slots) {
+    for (int ci = 0; ci < 6 && !found; ++ci) {
+      const int mtx = cand[ci][0], mty = cand[ci][1];
+      if (2 * mtx * mty * p.cout > 512) continue;
+      if (8 * mtx > round_up(W, 8) && mtx > 1) continue;
+      if (16 * mty > round_up(H, 16) && mty > 1) continue;
+      const int HP = 16 * mty + k - 1, WP = 8 * mtx + k - 1;
+      for (int gsplit = 1; gsplit <= 2 && !found; ++gsplit) {
+        if (gsplit == 2 && (p.cin % kGroupCh != 0)) continue;
+        const int gchunks = gsplit == 2 ? 4 : (ng64 == 1 ? p.cin : kGroupCh) / 8;
+        const int items = gsplit == 2 ? 2 * ng64 : ng64;
+        int plane = HP * WP * 16;
+        // producer store bank spreading: plane stride = 16*q (mod 128) with q = pixels per quarter-warp
+        const int q = gchunks >= 8 ? 1 : 8 / gchunks;
+        plane = (plane + 127) / 128 * 128 + 16 * q;
+        const int slot = plane * gchunks * (precision == 3 ? 2 : 1);
+        // k-blocks per weight stage: divides every item's k-block count, stage <= 16 KB
+        const int last_kb = gsplit == 2 ? 2 : ((p.cin - (ng64 - 1) * kGroupCh) >> 4);
+        const int full_kb = gsplit == 2 ? 2 : ((ng64 > 1 ? kGroupCh : p.cin) >> 4);
+        int kbs = 4;
+        while (kbs > 1 && (last_kb % kbs != 0 || full_kb % kbs != 0 || kbs * p.kb_bytes > 16384)) kbs >>= 1;
+        const int stage_bytes = kbs * p.kb_bytes;
+        const int stages_per_tile = k * k * (p.cin >> 4) / kbs;
+        for (int nst = kMaxStages; nst >= 2 && !found; --nst) {
+          if ((size_t)want_slots * slot + (size_t)nst * stage_bytes + 1024 > (size_t)smem_budget) continue;
+          p.mtx = mtx; p.mty = mty; p.nslots = want_slots; p.gsplit = gsplit; p.gchunks = gchunks; p.ngroups = items;
+          p.HP = HP; p.WP = WP; p.plane_bytes = plane; p.slot_bytes = slot;
+          p.kbs = kbs; p.stage_bytes = stage_bytes;
+          p.nstages = nst > stages_per_tile && stages_per_tile >= 1 ? (stages_per_tile < 2 ? 2 : stages_per_tile) : nst;
+          if (p.nstages > kMaxStages) p.nstages = kMaxStages;
+          found = true;
+        }
       }
     }
   }
-  CVD_CHECK_ARG(best_mtx > 0, "cvd_conv_fwd: no tile fits shared memory (cin=%d cout=%d k=%d)", cin, cout, k);
-  p.mtx = best_mtx; p.mty = best_mty; p.nslots = best_nslots; p.nstages = best_nst;
-  const int stages_total = k * k * (p.cin >> 4) / p.kbs;
-  if (p.nstages > stages_total) p.nstages = stages_total < 1 ? 1 : stages_total;
+  CVD_CHECK_ARG(found, "cvd_conv_fwd: no tile fits shared memory (cin=%d cout=%d k=%d)", cin, cout, k);
   p.tiles_x = (W + 8 * p.mtx - 1) / (8 * p.mtx);
   p.tiles_y = (H + 16 * p.mty - 1) / (16 * p.mty);
-  int cols = p.mtx * p.mty * p.cout, pw = 32;
+  p.ntiles = N * p.tiles_x * p.tiles_y;
+  int cols = 2 * p.mtx * p.mty * p.cout, pw = 32;
   while (pw < cols) pw <<= 1;
   p.tmem_cols = pw;
   CVD_CHECK_ARG(p.plane_bytes < (1 << 18) && p.WP * 16 < (1 << 18), "cvd_conv_fwd: descriptor offset overflow");
 
   const size_t smem = (size_t)p.nslots * p.slot_bytes + (size_t)p.nstages * p.stage_bytes + 1024;
-  const long long grid = (long long)N * p.tiles_x * p.tiles_y;
-  CVD_CHECK_ARG(grid < (1ll << 31), "cvd_conv_fwd: grid too large");
+  const long long grid = p.ntiles < cvd_num_sms() ? p.ntiles : cvd_num_sms();   // persistent: one CTA per SM
   const int MT = p.mtx * p.mty;
   cudaError_t e = cudaSuccess;
 #define CVD_CONV_LAUNCH(MTV, NS)                                                                             \

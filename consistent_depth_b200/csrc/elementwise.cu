@@ -38,11 +38,21 @@ bn_stats_kernel(const float* __restrict__ x, int c_total, int c0, int C, long lo
     const long long stride = (long long)gridDim.x * lanes;
     int cnt = 0;
     double ds[4] = {0, 0, 0, 0}, dss[4] = {0, 0, 0, 0};
-    for (long long p = (long long)blockIdx.x * lanes + pl; p < npix; p += stride) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(x + p * c_total + c0 + 4 * q));
-      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-      ss[0] = fmaf(v.x, v.x, ss[0]); ss[1] = fmaf(v.y, v.y, ss[1]); ss[2] = fmaf(v.z, v.z, ss[2]); ss[3] = fmaf(v.w, v.w, ss[3]);
-      if (++cnt == 64) {                           // bound fp32 partial sums to 64 terms
+    // 4 independent 128-bit loads in flight per thread (the pass is pure streaming: latency must be hidden)
+    for (long long p0 = (long long)blockIdx.x * lanes + pl; p0 < npix; p0 += 4 * stride) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long p = p0 + u * stride;
+        v[u] = p < npix ? __ldg(reinterpret_cast<const float4*>(x + p * c_total + c0 + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w;
+        ss[0] = fmaf(v[u].x, v[u].x, ss[0]); ss[1] = fmaf(v[u].y, v[u].y, ss[1]);
+        ss[2] = fmaf(v[u].z, v[u].z, ss[2]); ss[3] = fmaf(v[u].w, v[u].w, ss[3]);
+      }
+      if (++cnt == 16) {                           // bound fp32 partial sums to 64 terms
 #pragma unroll
         for (int i = 0; i < 4; ++i) { ds[i] += s[i]; dss[i] += ss[i]; s[i] = 0.f; ss[i] = 0.f; }
         cnt = 0;
@@ -119,15 +129,25 @@ bn_bwd_reduce_kernel(const float* __restrict__ x, int x_ct, int x_c0,
     double ds[4] = {0, 0, 0, 0}, dsy[4] = {0, 0, 0, 0};
     int cnt = 0;
     const long long stride = (long long)gridDim.x * lanes;
-    for (long long p = (long long)blockIdx.x * lanes + pl; p < npix; p += stride) {
-      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + p * x_ct + x_c0 + 4 * q));
-      const float4 dv = __ldg(reinterpret_cast<const float4*>(dy + p * dy_ct + dc));
-      const float y0 = fmaf(av.x, xv.x, bv.x), y1 = fmaf(av.y, xv.y, bv.y), y2 = fmaf(av.z, xv.z, bv.z), y3 = fmaf(av.w, xv.w, bv.w);
-      const float g0 = (!relu || y0 > 0.f) ? dv.x : 0.f, g1 = (!relu || y1 > 0.f) ? dv.y : 0.f;
-      const float g2 = (!relu || y2 > 0.f) ? dv.z : 0.f, g3 = (!relu || y3 > 0.f) ? dv.w : 0.f;
-      s[0] += g0; s[1] += g1; s[2] += g2; s[3] += g3;
-      sy[0] = fmaf(g0, y0, sy[0]); sy[1] = fmaf(g1, y1, sy[1]); sy[2] = fmaf(g2, y2, sy[2]); sy[3] = fmaf(g3, y3, sy[3]);
-      if (++cnt == 64) {
+    for (long long p0 = (long long)blockIdx.x * lanes + pl; p0 < npix; p0 += 4 * stride) {
+      float4 xq[4], dq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long p = p0 + u * stride;
+        const bool ok = p < npix;
+        xq[u] = ok ? __ldg(reinterpret_cast<const float4*>(x + p * x_ct + x_c0 + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dq[u] = ok ? __ldg(reinterpret_cast<const float4*>(dy + p * dy_ct + dc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 xv = xq[u], dv = dq[u];
+        const float y0 = fmaf(av.x, xv.x, bv.x), y1 = fmaf(av.y, xv.y, bv.y), y2 = fmaf(av.z, xv.z, bv.z), y3 = fmaf(av.w, xv.w, bv.w);
+        const float g0 = (!relu || y0 > 0.f) ? dv.x : 0.f, g1 = (!relu || y1 > 0.f) ? dv.y : 0.f;
+        const float g2 = (!relu || y2 > 0.f) ? dv.z : 0.f, g3 = (!relu || y3 > 0.f) ? dv.w : 0.f;
+        s[0] += g0; s[1] += g1; s[2] += g2; s[3] += g3;
+        sy[0] = fmaf(g0, y0, sy[0]); sy[1] = fmaf(g1, y1, sy[1]); sy[2] = fmaf(g2, y2, sy[2]); sy[3] = fmaf(g3, y3, sy[3]);
+      }
+      if (++cnt == 16) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) { ds[i] += s[i]; dsy[i] += sy[i]; s[i] = 0.f; sy[i] = 0.f; }
         cnt = 0;

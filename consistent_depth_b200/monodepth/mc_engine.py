@@ -210,6 +210,8 @@ class McEngine:
         self._conv(z, "pred_layer.weight", "pred_layer.bias", _T(self.depth), 64, 1, 3, N, H, W, flags=ops.FLAG_EXP)
         self.recs.append(("pred", z))
         self._emit_backward()
+        self.pack_fwd_tab = ops.make_pack_table(self.pack_fwd, self.dev)
+        self.pack_bwd_tab = ops.make_pack_table(self.pack_bwd, self.dev)
 
     # forward helpers ------------------------------------------------------
     def _conv(self, x, wkey, bkey, dst, cin, cout, k, N, h, w, flags=0, wshape=None):
@@ -217,7 +219,7 @@ class McEngine:
         bias = self._p(bkey, n=cout, shape=(cout,))
         pk = self._packed(cin, cout, k)
         prec = self.prec
-        self.pack_fwd.append(lambda: ops.pack_weights(Wt, False, prec, pk))
+        self.pack_fwd.append((Wt, pk, False))
         self.raw_outputs[wkey[:-7]] = (dst.buf, dst.off, cout)       # conv prefix -> where its raw output lives
         s, d = x.src(), ops.make_dst(dst.view())
         self.fwd.append(lambda: ops.conv(s, pk, bias, d, N, h, w, cin, cout, k, prec, flags))
@@ -325,7 +327,7 @@ class McEngine:
                 H, W = self.H, self.W
                 Wt = self._p("pred_layer.weight")
                 pkt = self._packed(1, 64, 3)
-                self.pack_bwd.append(lambda Wt=Wt, pkt=pkt: ops.pack_weights(Wt, True, prec, pkt))
+                self.pack_bwd.append((Wt, pkt, True))
                 dld = _T(self.dld4, C=1)
                 gs, xs = dld.src(), z.src()
                 dW, db = self._g("pred_layer.weight"), self._g("pred_layer.bias")
@@ -363,7 +365,7 @@ class McEngine:
                 for i in range(3):
                     Wt = self._p(f"{prefix}.convs.{i + 1}.3.weight")
                     pkt = self._packed(Bs[i], As[i], ks[i])
-                    self.pack_bwd.append(lambda Wt=Wt, pkt=pkt: ops.pack_weights(Wt, True, prec, pkt))
+                    self.pack_bwd.append((Wt, pkt, True))
                     gs, xs = outs[i].bnbwd_src(), mids[i].src()
                     dW = self._g(f"{prefix}.convs.{i + 1}.3.weight")
                     self.bwd.append(lambda gs=gs, xs=xs, dW=dW, ci=As[i], co=Bs[i], k=ks[i], h=h, w=w:
@@ -382,7 +384,7 @@ class McEngine:
                                 ops.conv_wgrad(gs, xs, dW1, N, h, w, cin, co, 1, prec))
                 if x.dbuf is not None:
                     pkt = self._packed(o0 + A, cin, 1)
-                    self.pack_bwd.append(lambda W1=W1, pkt=pkt: ops.pack_weights(W1, True, prec, pkt))
+                    self.pack_bwd.append((W1, pkt, True))
                     d = ops.make_dst(x.dview())
                     fl = ops.FLAG_ACCUM if x.grad_written else 0
                     self.bwd.append(lambda gs=gs, pkt=pkt, d=d, fl=fl, ci=o0 + A, co=cin, h=h, w=w:
@@ -404,8 +406,7 @@ class McEngine:
         """images (N,3,H,W) BGR in [0,1] (CUDA, contiguous) -> depth (N,H,W) (engine-owned buffer)."""
         assert images.shape == (self.N, 3, self.H, self.W), images.shape
         ops.image_to_nhwc4(images.contiguous(), self.img4, self.N, self.H, self.W)
-        for f in self.pack_fwd:
-            f()
+        ops.pack_batch(self.pack_fwd_tab[0], self.pack_fwd_tab[1], self.prec)
         for f in self.fwd:
             f()
         if self.train_mode:
@@ -415,7 +416,6 @@ class McEngine:
     def backward(self, grad_depth):
         """grad_depth (N,H,W): d loss / d depth.  Accumulates into grad_flat (zero it first, as opt.zero_grad does)."""
         self.grad_depth = grad_depth.contiguous()
-        for f in self.pack_bwd:
-            f()
+        ops.pack_batch(self.pack_bwd_tab[0], self.pack_bwd_tab[1], self.prec)
         for f in self.bwd:
             f()

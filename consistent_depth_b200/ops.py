@@ -142,3 +142,19 @@ def image_to_nhwc4(img, out, N, H, W):
 def dlogdepth(grad_depth, depth, out4, dbias=None):
     _lib.check(_lib.lib().cvd_dlogdepth(_lib.ptr(grad_depth), _lib.ptr(depth), _lib.ptr(out4),
                                         C.c_longlong(depth.numel()), _lib.ptr(dbias), _lib.stream()), "cvd_dlogdepth")
+
+
+def make_pack_table(entries, device):
+    """entries: [(w_oihw tensor, packed uint8 tensor, transpose_flip)] -> device descriptor table for pack_batch."""
+    import numpy as np
+    dt = np.dtype([("w", "<u8"), ("out", "<u8"), ("cin", "<i4"), ("cout", "<i4"), ("k", "<i4"), ("flip", "<i4")])
+    arr = np.zeros(len(entries), dtype=dt)
+    for i, (w, out, flip) in enumerate(entries):
+        arr[i] = (w.data_ptr(), out.data_ptr(), w.shape[1], w.shape[0], w.shape[2], 1 if flip else 0)
+    t = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
+    t._keep = [e[0] for e in entries] + [e[1] for e in entries]
+    return t, len(entries)
+
+
+def pack_batch(table, n, precision):
+    _lib.check(_lib.lib().cvd_conv_pack_batch(_lib.ptr(table), n, precision, _lib.stream()), "cvd_conv_pack_batch")

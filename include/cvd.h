@@ -140,6 +140,10 @@ size_t cvd_conv_packed_bytes(int cin, int cout, int k, int precision);
 int cvd_conv_pack_weights(const float* w_oihw, int cin, int cout, int k, int transpose_flip,
                           int precision, void* packed, void* stream);
 
+/* The same packing for n convolutions in one launch.  descs_dev: device array of
+ * { const float* w_oihw; void* packed; int cin; int cout; int k; int transpose_flip; } (32 bytes each). */
+int cvd_conv_pack_batch(const void* descs_dev, int n, int precision, void* stream);
+
 /* Convolution, stride 1, "same" zero padding, over N images of HxW: replaces
  * nn.Conv2d forward (hourglass.py:27,39,42,164,173).  With transpose_flip
  * weights (cin/cout given in GEMM terms: cin = channels of the tensor being
