@@ -39,20 +39,20 @@ bn_stats_kernel(const float* __restrict__ x, int c_total, int c0, int C, long lo
     int cnt = 0;
     double ds[4] = {0, 0, 0, 0}, dss[4] = {0, 0, 0, 0};
     // 4 independent 128-bit loads in flight per thread (the pass is pure streaming: latency must be hidden)
-    for (long long p0 = (long long)blockIdx.x * lanes + pl; p0 < npix; p0 += 4 * stride) {
-      float4 v[4];
+    for (long long p0 = (long long)blockIdx.x * lanes + pl; p0 < npix; p0 += 8 * stride) {
+      float4 v[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const long long p = p0 + u * stride;
         v[u] = p < npix ? __ldg(reinterpret_cast<const float4*>(x + p * c_total + c0 + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w;
         ss[0] = fmaf(v[u].x, v[u].x, ss[0]); ss[1] = fmaf(v[u].y, v[u].y, ss[1]);
         ss[2] = fmaf(v[u].z, v[u].z, ss[2]); ss[3] = fmaf(v[u].w, v[u].w, ss[3]);
       }
-      if (++cnt == 16) {                           // bound fp32 partial sums to 64 terms
+      if (++cnt == 8) {                            // bound fp32 partial sums to 64 terms
 #pragma unroll
         for (int i = 0; i < 4; ++i) { ds[i] += s[i]; dss[i] += ss[i]; s[i] = 0.f; ss[i] = 0.f; }
         cnt = 0;
@@ -396,7 +396,7 @@ extern "C" int cvd_bn_stats(const float* x, int c_total, int c_off, int C, long 
                 "cvd_bn_stats: bad channels C=%d c_off=%d c_total=%d", C, c_off, c_total);
   const int lanes = 256 / (C >> 2);
   long long blocks = (npix + lanes * 64 - 1) / ((long long)lanes * 64);
-  const long long cap = (long long)cvd_num_sms() * 8;
+  const long long cap = (long long)cvd_num_sms() * 2;       // few blocks: the f64 atomics per block are the tail cost
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   bn_stats_kernel<<<(unsigned)blocks, 256, 2 * C * sizeof(double), (cudaStream_t)stream>>>(
@@ -417,7 +417,7 @@ extern "C" int cvd_bn_bwd_reduce(const float* x, int x_ctotal, int x_coff,
                 "cvd_bn_bwd_reduce: bad channels");
   const int lanes = 256 / (C >> 2);
   long long blocks = (npix + lanes * 64 - 1) / ((long long)lanes * 64);
-  const long long cap = (long long)cvd_num_sms() * 8;
+  const long long cap = (long long)cvd_num_sms() * 3;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   bn_bwd_reduce_kernel<<<(unsigned)blocks, 256, 2 * C * sizeof(double), (cudaStream_t)stream>>>(

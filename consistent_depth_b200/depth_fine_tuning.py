@@ -15,6 +15,7 @@ import torch
 from torch.utils.data import DataLoader
 
 from . import optimizer
+from .distributed import global_focal, shard_slice
 from .fine_tune_step import FineTuneStep
 from .loaders.video_dataset import VideoDataset, VideoFrameDataset
 from .loss.joint_loss import JointLoss
@@ -130,12 +131,12 @@ class DepthFineTuner:
                     if nb == 0:
                         continue
                 bl = nb // self.world
-                sl = slice(self.rank * bl, (self.rank + 1) * bl)
+                sl = shard_slice(nb, self.rank, self.world)
                 geom = metadata["geometry_consistency"]
                 step = get_step(bl)
                 f_dir = None
                 if self.world > 1:
-                    f_dir = (float(metadata["intrinsics"][:nb, 0, :2].mean()), float(metadata["intrinsics"][:nb, 1, :2].mean()))
+                    f_dir = global_focal(metadata["intrinsics"], nb)
                 step.load_batch(images[sl], [f[sl] for f in geom["flows"]], [m[sl] for m in geom["masks"]],
                                 metadata["extrinsics"][sl], metadata["intrinsics"][sl], f_dir)
                 loss = step.step()

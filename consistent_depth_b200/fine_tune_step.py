@@ -19,6 +19,7 @@ import ctypes as C
 import torch
 
 from . import _lib, ops
+from .distributed import allreduce_flat
 from .utils.geometry import _Workspace
 
 
@@ -124,7 +125,6 @@ class FineTuneStep:
         self.adam_state.copy_(keep[4]); P.num_batches_tracked = keep[5]
 
     def _step_distributed(self):
-        import torch.distributed as dist
         P = self.model.P
         if self.graph is None and self.use_graph:
             n0 = _lib.launch_count()
@@ -142,6 +142,6 @@ class FineTuneStep:
         else:
             self._fwd_bwd()
         # ONE all-reduce over NVLink: [flat gradient | local loss (already divided by B_global)], in place
-        dist.all_reduce(P.grad_store, op=dist.ReduceOp.SUM, group=self.pg)
+        allreduce_flat(P.grad_store, self.pg)
         self._adam(self.loss)
         return self.loss
