@@ -21,11 +21,11 @@
 // Precision: bf16 tensor cores with the operands split v = hi + lo (3 MMAs: hi*hi, lo*hi, hi*lo,
 // fp32 accumulate in TMEM) => fp32-class results ("precision 3"), or plain bf16 ("precision 1").
 //
-// Persistent, warp-specialised pipeline (one CTA per SM, 320 threads, each CTA loops over output tiles):
+// Persistent, warp-specialised pipeline (one CTA per SM, 448 threads, each CTA loops over output tiles):
 //   warp 0      TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma / commit)
 //   warp 1      weight streamer: cp.async.bulk of pre-packed core-matrix blobs through an mbarrier ring
-//   warps 2-5   activation producers: global -> transform -> bf16 hi/lo -> smem slot (ring of 1-2 slots)
-//   warps 6-9   epilogue: tcgen05.ld -> +bias / exp -> NHWC global stores
+//   warps 2-9   activation producers: global -> transform -> bf16 hi/lo -> smem slot (ring of 1-2 slots)
+//   warps 10-13 epilogue: tcgen05.ld -> +bias / exp -> NHWC global stores
 // Two TMEM accumulator buffers and the slot ring let tile t's epilogue, tile t+1's MMAs and tile t+2's
 // activation staging run concurrently; for large filters the 64 input channels are staged as two
 // 32-channel slots so staging overlaps the MMAs even when one full-depth halo tile is all that fits.
@@ -35,8 +35,8 @@
 
 namespace {
 
-constexpr int kThreads = 320;
-constexpr int kProducerThreads = 128;
+constexpr int kThreads = 448;
+constexpr int kProducerThreads = 256;
 constexpr int kMaxStages = 8;
 constexpr int kGroupCh = 64;          // channels per activation group resident in one A slot
 
@@ -196,7 +196,7 @@ conv_tc_kernel(const ConvArgs p)
       }
     }
     __syncwarp();
-  } else if (warp < 6) {
+  } else if (warp < 10) {
     // ============================ activation producers ============================
     const int tid = threadIdx.x - 64;
     int item = 0;
@@ -208,7 +208,7 @@ conv_tc_kernel(const ConvArgs p)
       for (int g = 0; g < p.ngroups; ++g, ++item) {
         const int slot = item % p.nslots;
         if (item >= p.nslots) tc::mbar_wait(&a_empty[slot], (uint32_t)(((item / p.nslots) - 1) & 1));
-        fillns::fill_window(p.src, a_slots + (size_t)slot * p.slot_bytes, p.plane_bytes, p.gchunks * p.plane_bytes, p.nsplit,
+        fillns::fill_window<kProducerThreads>(p.src, a_slots + (size_t)slot * p.slot_bytes, p.plane_bytes, p.gchunks * p.plane_bytes, p.nsplit,
                             n, p.H, p.W, oy - p.pad, ox - p.pad, p.HP, p.WP, item_cfirst(g), item_chunks(g), tid);
         tc::fence_proxy_async_smem();
         tc::mbar_arrive(&a_full[slot]);

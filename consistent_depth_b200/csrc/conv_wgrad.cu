@@ -17,11 +17,12 @@
 #include "cvd_common.cuh"
 #include "tc_common.cuh"
 #include "fill.cuh"
+#include <cstdlib>
 
 namespace {
 
-constexpr int kThreads = 192;
-constexpr int kProducerThreads = 128;
+constexpr int kThreads = 320;            // warp 0 issuer, warp 1 idle, warps 2-9 producers (2-5 also epilogue)
+constexpr int kProducerThreads = 256;
 constexpr int TW = 16;                 // pixel-tile width = one K=16 step per tile row
 
 using fillns::SrcView;
@@ -134,12 +135,12 @@ wgrad_tc_kernel(const WgArgs p)
       const int oy = ty * p.TH, ox = tx * TW;
       uint8_t* xs = stages + (size_t)st * p.stage_bytes;
       uint8_t* gs = xs + p.x_bytes;
-      fillns::fill_window(p.x, xs, p.x_plane, x_lo, p.nsplit, n, p.H, p.W, oy + ky0 - p.pad, ox - p.pad, p.xHP, p.xWP, 0, p.x_chunks, tid);
-      fillns::fill_window(p.g, gs, p.g_plane, g_lo, p.nsplit, n, p.H, p.W, oy, ox, p.TH, TW, 0, p.g_chunks, tid);
+      fillns::fill_window<kProducerThreads>(p.x, xs, p.x_plane, x_lo, p.nsplit, n, p.H, p.W, oy + ky0 - p.pad, ox - p.pad, p.xHP, p.xWP, 0, p.x_chunks, tid);
+      fillns::fill_window<kProducerThreads>(p.g, gs, p.g_plane, g_lo, p.nsplit, n, p.H, p.W, oy, ox, p.TH, TW, 0, p.g_chunks, tid);
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&full[st]);
     }
-    if (my_tiles > 0) {
+    if (my_tiles > 0 && warp < 6) {
       // -------- epilogue: RED the partial dW of this CTA's taps
       tc::mbar_wait(acc_full, 0);
       tc::tc_fence_after();
@@ -185,12 +186,25 @@ SrcView make_view(const cvd_src_t* s, int cvalid) {
 
 }  // namespace
 
+int cvd_conv_wgrad_kx(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oihw,
+                      int N, int H, int W, int cin, int cout, int k, int precision, void* stream);   // conv_wgrad_kx.cu
+
 extern "C" int cvd_conv_wgrad(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oihw,
                               int N, int H, int W, int cin, int cout, int k, int precision, void* stream)
 {
   CVD_CHECK_ARG(gsrc && xsrc && dw_oihw && gsrc->x && xsrc->x, "cvd_conv_wgrad: null pointer");
   CVD_CHECK_ARG(precision == 1 || precision == 3, "cvd_conv_wgrad: precision must be 1 or 3");
   CVD_CHECK_ARG(k >= 1 && k <= 11 && (k & 1), "cvd_conv_wgrad: k=%d unsupported", k);
+  // kx-fused variant (conv_wgrad_kx.cu): measured faster only when the shifted operand is a single 8-channel chunk
+  // (the 3-channel image of the first layer: 0.45 ms vs 1.58 ms); elsewhere its extra staging (more tap groups,
+  // wider halo) makes it producer-bound, so the per-tap kernel stays the default.  CVD_WGRAD_KX=all forces it.
+  const char* kxenv = getenv("CVD_WGRAD_KX");
+  const bool kx_all = kxenv && kxenv[0] == 'a';
+  const int cmin = cin < cout ? cin : cout;
+  if (k >= 3 && !getenv("CVD_WGRAD_PER_TAP") && (kx_all || cmin <= 8)) {
+    const int rc = cvd_conv_wgrad_kx(gsrc, xsrc, dw_oihw, N, H, W, cin, cout, k, precision, stream);
+    if (rc != 2) return rc;
+  }
   WgArgs p{};
   p.g = make_view(gsrc, round_up(cout, 4)); p.x = make_view(xsrc, round_up(cin, 4));
   p.dw = dw_oihw; p.N = N; p.H = H; p.W = W; p.k = k; p.pad = (k - 1) / 2;

@@ -2,7 +2,7 @@
 // global NHWC fp32 (through a channel view) -> per-channel transform -> bf16 hi/lo -> shared memory in the
 // UMMA SWIZZLE_NONE canonical layout  [8-channel chunk][window row][window col][16 B].
 //
-// 128 producer threads; a thread owns ONE 8-channel chunk for the whole call (128 % nchunks == 0), so the
+// kProducers (128-256) producer threads; a thread owns ONE 8-channel chunk for the whole call (kProducers % nchunks == 0), so the
 // per-channel constants (BatchNorm scale/shift, backward constants) are loaded into registers once, and
 // walks the window pixels with stride 128/nchunks.  Loads are issued UNROLL items ahead of the math so
 // several 128-bit requests per thread are in flight (the window is read once; latency, not bandwidth, is
@@ -13,7 +13,6 @@
 
 namespace fillns {
 
-constexpr int kProducers = 128;
 
 struct SrcView {
   const float* x; const float* dy; const float* a; const float* b; const float4* bw;
@@ -24,10 +23,10 @@ __device__ __forceinline__ int vphys(int c, int c0, int n0, int gap) { return c0
 
 // Stage window pixels (r, c), r < rows, c < cols  <->  image pixel (y0 + r, x0 + c) of image n, logical channels
 // [cfirst, cfirst + 8*nchunks).  Out-of-image pixels and channels >= cvalid are zero.  nchunks in {1,2,4,8}.
-template <int MODE, int UNROLL>
+template <int MODE, int UNROLL, int kProducers>
 __device__ __forceinline__ void fill_window_impl(const SrcView& s, uint8_t* dst, int plane_bytes, int lo_off, int nsplit,
                                                  int n, int H, int W, int y0, int x0, int rows, int cols,
-                                                 int cfirst, int nchunks, int tid)
+                                                 int cfirst, int nchunks, int tid, int vx0, int vx1)
 {
   const int c8 = tid % nchunks;
   const int ppi = kProducers / nchunks;            // window pixels advanced per iteration
@@ -68,7 +67,7 @@ __device__ __forceinline__ void fill_window_impl(const SrcView& s, uint8_t* dst,
     for (int u = 0; u < UNROLL; ++u) {
       hps[u] = hp;
       const int iy = y0 + r, ix = x0 + c;
-      ok[u] = hp < npix && ch_ok && iy >= 0 && iy < H && ix >= 0 && ix < W;
+      ok[u] = hp < npix && ch_ok && iy >= 0 && iy < H && ix >= vx0 && ix < vx1;
       xa[u] = z4; xb[u] = z4; da[u] = z4; db[u] = z4;
       if (ok[u]) {
         const size_t pix = img_off + (size_t)iy * W + ix;
@@ -123,21 +122,25 @@ __device__ __forceinline__ void fill_window_impl(const SrcView& s, uint8_t* dst,
   }
 }
 
+template <int kProducers = 128>
 __device__ __forceinline__ void fill_window(const SrcView& s, uint8_t* dst, int plane_bytes, int lo_off, int nsplit,
                                             int n, int H, int W, int y0, int x0, int rows, int cols,
-                                            int cfirst, int nchunks, int tid)
+                                            int cfirst, int nchunks, int tid, int vx0 = 0, int vx1 = 1 << 30)
 {
+  // [vx0, vx1): image columns that may be non-zero (default: the whole image)
+  vx0 = vx0 < 0 ? 0 : vx0;
+  vx1 = vx1 > W ? W : vx1;
   // chunk counts that do not divide 128 (e.g. 26 chunks = 208 channels) are staged in power-of-two batches
   int done = 0;
   while (done < nchunks) {
     int batch = 8;
     while (batch > nchunks - done) batch >>= 1;
     if (s.mode == CVD_XF_AFFINE)
-      fill_window_impl<CVD_XF_AFFINE, 4>(s, dst + (size_t)done * plane_bytes, plane_bytes, lo_off, nsplit, n, H, W, y0, x0, rows, cols,
-                                         cfirst + done * 8, batch, tid);
+      fill_window_impl<CVD_XF_AFFINE, 4, kProducers>(s, dst + (size_t)done * plane_bytes, plane_bytes, lo_off, nsplit, n, H, W, y0, x0, rows, cols,
+                                         cfirst + done * 8, batch, tid, vx0, vx1);
     else
-      fill_window_impl<CVD_XF_BNBWD, 2>(s, dst + (size_t)done * plane_bytes, plane_bytes, lo_off, nsplit, n, H, W, y0, x0, rows, cols,
-                                        cfirst + done * 8, batch, tid);
+      fill_window_impl<CVD_XF_BNBWD, 2, kProducers>(s, dst + (size_t)done * plane_bytes, plane_bytes, lo_off, nsplit, n, H, W, y0, x0, rows, cols,
+                                        cfirst + done * 8, batch, tid, vx0, vx1);
     done += batch;
   }
 }
