@@ -8,7 +8,10 @@ from consistent_depth_b200.synthetic import SyntheticVideo
 H, W, BS = 224, 384, 4
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 dev = torch.device("cuda:0")
-model = MannequinChallengeModel()
+import math
+from consistent_depth_b200.monodepth.mannequin_challenge_model import default_init_state
+sd = default_init_state(0); sd['pred_layer.weight'] = sd['pred_layer.weight'] * 0.1; sd['pred_layer.bias'] = torch.full((1,), math.log(2.0))
+model = MannequinChallengeModel(state_dict=sd)
 video = SyntheticVideo(50, H, W, dev, seed=1236)
 step = FineTuneStep(model, BS, H, W, lr=model.learning_rate, use_graph=(os.environ.get("GRAPH", "1") == "1"))
 g = torch.Generator().manual_seed(0)
