@@ -21,11 +21,11 @@
 // Precision: bf16 tensor cores with the operands split v = hi + lo (3 MMAs: hi*hi, lo*hi, hi*lo,
 // fp32 accumulate in TMEM) => fp32-class results ("precision 3"), or plain bf16 ("precision 1").
 //
-// Persistent, warp-specialised pipeline (one CTA per SM, 448 threads, each CTA loops over output tiles):
-//   warp 0      TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma / commit)
-//   warp 1      weight streamer: cp.async.bulk of pre-packed core-matrix blobs through an mbarrier ring
-//   warps 2-9   activation producers: global -> transform -> bf16 hi/lo -> smem slot (ring of 1-2 slots)
-//   warps 10-13 epilogue: tcgen05.ld -> +bias / exp -> NHWC global stores
+// Persistent, warp-specialised pipeline (one CTA per SM, 480 threads, each CTA loops over output tiles):
+//   warps 0-1   MMA issuers (one elected lane each issues tcgen05.mma / commit; warp 0 also owns TMEM)
+//   warp 2      weight streamer: cp.async.bulk of pre-packed core-matrix blobs through an mbarrier ring
+//   warps 3-10  activation producers: global -> transform -> bf16 hi/lo -> smem slot (ring of 1-2 slots)
+//   warps 11-14 epilogue: tcgen05.ld -> +bias / exp -> NHWC global stores
 // Two TMEM accumulator buffers and the slot ring let tile t's epilogue, tile t+1's MMAs and tile t+2's
 // activation staging run concurrently; for large filters the 64 input channels are staged as two
 // 32-channel slots so staging overlaps the MMAs even when one full-depth halo tile is all that fits.
@@ -35,7 +35,8 @@
 
 namespace {
 
-constexpr int kThreads = 448;
+constexpr int kIssuers = 2;                // MMA issuer warps (M-tiles split between them)
+constexpr int kThreads = 32 * (kIssuers + 1 + 8 + 4);   // issuers | weight streamer | 8 producer warps | 4 epilogue warps
 constexpr int kProducerThreads = 256;
 constexpr int kMaxStages = 8;
 constexpr int kGroupCh = 64;          // channels per activation group resident in one A slot
@@ -82,10 +83,10 @@ conv_tc_kernel(const ConvArgs p)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.nstages; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < p.nstages; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], kIssuers); }
     for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&a_full[i], kProducerThreads); tc::mbar_init(&a_empty[i], 1);
-      tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 4);
+      tc::mbar_init(&a_full[i], kProducerThreads); tc::mbar_init(&a_empty[i], kIssuers);
+      tc::mbar_init(&acc_full[i], kIssuers); tc::mbar_init(&acc_empty[i], 4);
     }
     tc::mbar_fence_init();
   }
@@ -106,19 +107,25 @@ conv_tc_kernel(const ConvArgs p)
   auto item_chunks = [&](int it) { return p.gsplit == 2 ? 4 : min(p.gchunks, (p.cin - it * kGroupCh) >> 3); };
   (void)kb_full;
 
-  if (warp == 0) {
-    // ============================ MMA issuer ============================
+  if (warp < kIssuers) {
+    // ============================ MMA issuers ============================
+    // Two issuer warps, each owning half of the CTA's M-tiles (a single thread cannot issue the small-N MMAs
+    // fast enough; measured 1.5x on the wgrad kernel).  With one M-tile the second warp only keeps the protocol.
+    constexpr int MTW = MT >= kIssuers ? MT / kIssuers : MT;        // M-tiles per issuer warp
+    const int mt0 = MT >= kIssuers ? warp * MTW : 0;
+    const bool active = MT >= kIssuers || warp == 0;
     const uint32_t idesc = tc::idesc_bf16(128, p.cout, 0, 0);
     const uint32_t a_base = tc::smem_u32(a_slots), b_base = tc::smem_u32(b_stages);
     const uint32_t lo_a = (uint32_t)p.gchunks * p.plane_bytes;      // hi -> lo plane offset inside a slot
     const uint32_t lo_b = (uint32_t)p.cout * 32;                     // hi -> lo blob offset inside a k-block
     const uint64_t adesc0 = tc::smem_desc_base((uint32_t)p.plane_bytes, (uint32_t)p.WP * 16);
     const uint64_t bdesc0 = tc::smem_desc_base(128, 256);
-    uint32_t aoff[MT];
+    uint32_t aoff[MTW];
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
+    for (int i = 0; i < MTW; ++i) {
+      const int mt = mt0 + i;
       const int my = mt / p.mtx, mx = mt - my * p.mtx;
-      aoff[mt] = (uint32_t)((my * 16 * p.WP + mx * 8) * 16);
+      aoff[i] = (uint32_t)((my * 16 * p.WP + mx * 8) * 16);
     }
     int stage = 0; uint32_t bphase = 0;
     int item = 0, ti = 0;
@@ -142,15 +149,15 @@ conv_tc_kernel(const ConvArgs p)
               if (tc::elect_one()) {
                 uint32_t bs = b_base + (uint32_t)stage * p.stage_bytes;
                 uint32_t a_kb = a_row + (uint32_t)(2 * ks * p.kbs) * p.plane_bytes;
-                for (int j = 0; j < p.kbs; ++j, bs += p.kb_bytes, a_kb += 2 * p.plane_bytes) {
+                for (int j = 0; j < p.kbs && active; ++j, bs += p.kb_bytes, a_kb += 2 * p.plane_bytes) {
                   const uint64_t bd_hi = tc::smem_desc_at(bdesc0, bs), bd_lo = tc::smem_desc_at(bdesc0, bs + lo_b);
 #pragma unroll
-                  for (int mt = 0; mt < MT; ++mt) {
-                    const uint32_t d = dbase + (uint32_t)(mt * p.cout);
-                    const uint64_t ad_hi = tc::smem_desc_at(adesc0, a_kb + aoff[mt]);
+                  for (int i = 0; i < MTW; ++i) {
+                    const uint32_t d = dbase + (uint32_t)((mt0 + i) * p.cout);
+                    const uint64_t ad_hi = tc::smem_desc_at(adesc0, a_kb + aoff[i]);
                     tc::umma_f16(d, ad_hi, bd_hi, idesc, first);
                     if (NSPLIT == 3) {
-                      tc::umma_f16(d, tc::smem_desc_at(adesc0, a_kb + aoff[mt] + lo_a), bd_hi, idesc, 1u);
+                      tc::umma_f16(d, tc::smem_desc_at(adesc0, a_kb + aoff[i] + lo_a), bd_hi, idesc, 1u);
                       tc::umma_f16(d, ad_hi, bd_lo, idesc, 1u);
                     }
                   }
@@ -170,7 +177,7 @@ conv_tc_kernel(const ConvArgs p)
       if (tc::elect_one()) tc::umma_commit(&acc_full[buf]);     // this tile's accumulators complete
       __syncwarp();
     }
-  } else if (warp == 1) {
+  } else if (warp == kIssuers) {
     // ============================ weight streamer ============================
     if (lane == 0) {
       int stage = 0; uint32_t ephase = 0; long long issued = 0;
@@ -196,9 +203,9 @@ conv_tc_kernel(const ConvArgs p)
       }
     }
     __syncwarp();
-  } else if (warp < 10) {
+  } else if (warp < kIssuers + 9) {
     // ============================ activation producers ============================
-    const int tid = threadIdx.x - 64;
+    const int tid = threadIdx.x - 32 * (kIssuers + 1);
     int item = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       int t = tile;

@@ -21,7 +21,8 @@
 
 namespace {
 
-constexpr int kThreads = 320;            // warp 0 issuer, warp 1 idle, warps 2-9 producers (2-5 also epilogue)
+constexpr int kIssuers = 4;                // MMA issuer warps (taps split between them)
+constexpr int kThreads = 32 * (kIssuers + 8);   // warps [0,kIssuers) issue, then 8 producer warps (first 4 also epilogue)
 constexpr int kProducerThreads = 256;
 constexpr int TW = 16;                 // pixel-tile width = one K=16 step per tile row
 
@@ -64,8 +65,8 @@ wgrad_tc_kernel(const WgArgs p)
   const int my_tiles = (p.ntiles - slab + p.nslabs - 1) / p.nslabs;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&full[i], kProducerThreads); tc::mbar_init(&empty[i], 1); }
-    tc::mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&full[i], kProducerThreads); tc::mbar_init(&empty[i], kIssuers); }
+    tc::mbar_init(acc_full, kIssuers);
     tc::mbar_fence_init();
   }
   if (warp == 0) { tc::tmem_alloc_dyn(tmem_base_sh, (uint32_t)p.tmem_cols); tc::tmem_relinquish(); }
@@ -75,8 +76,12 @@ wgrad_tc_kernel(const WgArgs p)
   const uint32_t tmem_base = *tmem_base_sh;
   const int x_lo = p.x_chunks * p.x_plane, g_lo = p.g_chunks * p.g_plane;
 
-  if (warp == 0) {
-    // MMA issuer: uniform loop nest over the whole warp, one elected lane issues
+  if (warp < kIssuers) {
+    // SEVERAL MMA issuer warps (each: uniform loop nest, one elected lane issues): the taps of this CTA are split
+    // between them -- a single thread cannot issue these small MMAs fast enough to keep the tensor pipe busy
+    // (measured: 1 -> 2 issuers = 1.56x on the 64->16 11x11 layer).
+    const int th = (t1 - t0 + kIssuers - 1) / kIssuers;
+    const int w_t0 = min(t1, t0 + warp * th), w_t1 = min(t1, t0 + (warp + 1) * th);
     const uint32_t idesc = tc::idesc_bf16(p.Mrows, p.Ncols, 1, 1);   // both operands MN-major
     const uint32_t sbase = tc::smem_u32(stages);
     const uint32_t m_plane = p.x_is_m ? p.x_plane : p.g_plane, n_plane = p.x_is_m ? p.g_plane : p.x_plane;
@@ -91,10 +96,10 @@ wgrad_tc_kernel(const WgArgs p)
       const uint32_t gs = xs + (uint32_t)p.x_bytes;
       if (tc::elect_one()) {
         // taps t0..t1-1 in raster order without divisions; per tap a straight run of TH x MBLK x NSPLIT MMAs
-        int ky = ky0, kx = t0 - ky0 * p.k;
-        uint32_t dtap = tmem_base;
+        int ky = w_t0 / p.k, kx = w_t0 - ky * p.k;
+        uint32_t dtap = tmem_base + (uint32_t)((w_t0 - t0) * MBLK * p.Ncols);
         const uint32_t x_row = (uint32_t)p.xWP * 16;
-        for (int tap = t0; tap < t1; ++tap) {
+        for (int tap = w_t0; tap < w_t1; ++tap) {
           // X window pixel (r + ky - ky0, kx + c), G pixel (r, c), c = 0..15
           uint32_t xa = xs + (uint32_t)(((ky - ky0) * p.xWP + kx) * 16);
           uint32_t ga = gs;
@@ -124,8 +129,8 @@ wgrad_tc_kernel(const WgArgs p)
     }
     if (my_tiles > 0 && tc::elect_one()) tc::umma_commit(acc_full);
     __syncwarp();
-  } else if (warp >= 2) {
-    const int tid = threadIdx.x - 64;
+  } else {
+    const int tid = threadIdx.x - 32 * kIssuers;
     for (int it = 0; it < my_tiles; ++it) {
       const int st = it % p.nstages;
       if (it >= p.nstages) tc::mbar_wait(&empty[st], (uint32_t)(((it / p.nstages) - 1) & 1));
@@ -140,7 +145,7 @@ wgrad_tc_kernel(const WgArgs p)
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&full[st]);
     }
-    if (my_tiles > 0 && warp < 6) {
+    if (my_tiles > 0 && warp < kIssuers + 4) {
       // -------- epilogue: RED the partial dW of this CTA's taps
       tc::mbar_wait(acc_full, 0);
       tc::tc_fence_after();
