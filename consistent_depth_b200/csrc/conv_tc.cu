@@ -79,6 +79,8 @@ conv_tc_kernel(const ConvArgs p)
   uint64_t* acc_full = a_empty + 2;              // [2]
   uint64_t* acc_empty = acc_full + 2;            // [2]
   uint32_t* tmem_base_sh = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sparams = reinterpret_cast<float*>(bars + 32);           // per-channel constants, 5 x cin floats
+  fillns::stage_params(p.src, sparams, p.cin, threadIdx.x, kThreads);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -216,7 +218,7 @@ conv_tc_kernel(const ConvArgs p)
         const int slot = item % p.nslots;
         if (item >= p.nslots) tc::mbar_wait(&a_empty[slot], (uint32_t)(((item / p.nslots) - 1) & 1));
         fillns::fill_window<kProducerThreads>(p.src, a_slots + (size_t)slot * p.slot_bytes, p.plane_bytes, p.gchunks * p.plane_bytes, p.nsplit,
-                            n, p.H, p.W, oy - p.pad, ox - p.pad, p.HP, p.WP, item_cfirst(g), item_chunks(g), tid);
+                            n, p.H, p.W, oy - p.pad, ox - p.pad, p.HP, p.WP, item_cfirst(g), item_chunks(g), tid, sparams, p.cin);
         tc::fence_proxy_async_smem();
         tc::mbar_arrive(&a_full[slot]);
       }
@@ -428,7 +430,7 @@ extern "C" int cvd_conv_fwd(const cvd_src_t* src, const void* packed_w, const fl
         const int stage_bytes = kbs * p.kb_bytes;
         const int stages_per_tile = k * k * (p.cin >> 4) / kbs;
         for (int nst = kMaxStages; nst >= 2 && !found; --nst) {
-          if ((size_t)want_slots * slot + (size_t)nst * stage_bytes + 1024 > (size_t)smem_budget) continue;
+          if ((size_t)want_slots * slot + (size_t)nst * stage_bytes + 1024 + fillns::param_bytes(p.cin) > (size_t)smem_budget) continue;
           p.mtx = mtx; p.mty = mty; p.nslots = want_slots; p.gsplit = gsplit; p.gchunks = gchunks; p.ngroups = items;
           p.HP = HP; p.WP = WP; p.plane_bytes = plane; p.slot_bytes = slot;
           p.kbs = kbs; p.stage_bytes = stage_bytes;
@@ -448,7 +450,7 @@ extern "C" int cvd_conv_fwd(const cvd_src_t* src, const void* packed_w, const fl
   p.tmem_cols = pw;
   CVD_CHECK_ARG(p.plane_bytes < (1 << 18) && p.WP * 16 < (1 << 18), "cvd_conv_fwd: descriptor offset overflow");
 
-  const size_t smem = (size_t)p.nslots * p.slot_bytes + (size_t)p.nstages * p.stage_bytes + 1024;
+  const size_t smem = (size_t)p.nslots * p.slot_bytes + (size_t)p.nstages * p.stage_bytes + 1024 + fillns::param_bytes(p.cin);
   const long long grid = p.ntiles < cvd_num_sms() ? p.ntiles : cvd_num_sms();   // persistent: one CTA per SM
   const int MT = p.mtx * p.mty;
   cudaError_t e = cudaSuccess;

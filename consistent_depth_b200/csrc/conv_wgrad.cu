@@ -54,6 +54,10 @@ wgrad_tc_kernel(const WgArgs p)
   uint64_t* empty = bars + 2;       // [2]
   uint64_t* acc_full = bars + 4;
   uint32_t* tmem_base_sh = reinterpret_cast<uint32_t*>(bars + 5);
+  float* xparams = reinterpret_cast<float*>(bars + 16);           // per-channel constants of X (5 x cin) then G (5 x cout)
+  float* gparams = xparams + 5 * p.cin;
+  fillns::stage_params(p.x, xparams, p.cin, threadIdx.x, kThreads);
+  fillns::stage_params(p.g, gparams, p.cout, threadIdx.x, kThreads);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int group = blockIdx.y, slab = blockIdx.x;
@@ -140,8 +144,8 @@ wgrad_tc_kernel(const WgArgs p)
       const int oy = ty * p.TH, ox = tx * TW;
       uint8_t* xs = stages + (size_t)st * p.stage_bytes;
       uint8_t* gs = xs + p.x_bytes;
-      fillns::fill_window<kProducerThreads>(p.x, xs, p.x_plane, x_lo, p.nsplit, n, p.H, p.W, oy + ky0 - p.pad, ox - p.pad, p.xHP, p.xWP, 0, p.x_chunks, tid);
-      fillns::fill_window<kProducerThreads>(p.g, gs, p.g_plane, g_lo, p.nsplit, n, p.H, p.W, oy, ox, p.TH, TW, 0, p.g_chunks, tid);
+      fillns::fill_window<kProducerThreads>(p.x, xs, p.x_plane, x_lo, p.nsplit, n, p.H, p.W, oy + ky0 - p.pad, ox - p.pad, p.xHP, p.xWP, 0, p.x_chunks, tid, xparams, p.cin);
+      fillns::fill_window<kProducerThreads>(p.g, gs, p.g_plane, g_lo, p.nsplit, n, p.H, p.W, oy, ox, p.TH, TW, 0, p.g_chunks, tid, gparams, p.cout);
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&full[st]);
     }
@@ -227,7 +231,7 @@ extern "C" int cvd_conv_wgrad(const cvd_src_t* gsrc, const cvd_src_t* xsrc, floa
   if (p.taps_per_group > taps) p.taps_per_group = taps;
   p.ngroups = (taps + p.taps_per_group - 1) / p.taps_per_group;
   // smem: choose the tile height so two stages fit
-  const int budget = 200 * 1024;
+  const int budget = 218 * 1024;
   p.x_chunks = p.cin / 8; p.g_chunks = p.cout / 8;
   // M operand is read with Mrows/8 chunk planes per block: make sure those reads stay inside the stage
   const int max_ky_span = (p.taps_per_group + k - 2) / k + 1;     // rows of taps a group can touch
@@ -239,7 +243,7 @@ extern "C" int cvd_conv_wgrad(const cvd_src_t* gsrc, const cvd_src_t* xsrc, floa
     const int m_chunks_read = p.mblk * (p.Mrows / 8);
     const int xb = xpl * (p.x_is_m ? (m_chunks_read > p.x_chunks ? m_chunks_read : p.x_chunks) : p.x_chunks) * (precision == 3 ? 2 : 1);
     const int gb = gpl * (!p.x_is_m ? (m_chunks_read > p.g_chunks ? m_chunks_read : p.g_chunks) : p.g_chunks) * (precision == 3 ? 2 : 1);
-    if (2 * (xb + gb) + 1024 <= budget) {
+    if (2 * (xb + gb) + 1024 + fillns::param_bytes(p.cin + p.cout) <= budget) {
       TH = th; p.xHP = xHP; p.xWP = xWP; p.x_plane = xpl; p.g_plane = gpl; p.x_bytes = xb; p.g_bytes = gb;
       break;
     }
@@ -256,7 +260,7 @@ extern "C" int cvd_conv_wgrad(const cvd_src_t* gsrc, const cvd_src_t* xsrc, floa
   int cols = p.taps_per_group * p.mblk * p.Ncols, pw = 32;
   while (pw < cols) pw <<= 1;
   p.tmem_cols = pw;
-  const size_t smem = (size_t)p.nstages * p.stage_bytes + 1024;
+  const size_t smem = (size_t)p.nstages * p.stage_bytes + 1024 + fillns::param_bytes(p.cin + p.cout);
   cudaError_t e = cudaSuccess;
 #define CVD_WG_LAUNCH(MB, NS)                                                                                 \
   do {                                                                                                        \

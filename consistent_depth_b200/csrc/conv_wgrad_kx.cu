@@ -29,7 +29,7 @@ using fillns::SrcView;
 struct KxArgs {
   SrcView g, x;
   float* dw;
-  int N, H, W, cin_w, cout_w, k, pad;
+  int N, H, W, cin_w, cout_w, k, pad, cin_p, cout_p;
   int nsplit;
   int n_is_g;                 // 1: N operand = G (Cin >= Cout), 0: N operand = X
   int Mrows;                  // 64 or 128 (channels of the M operand, padded)
@@ -55,6 +55,10 @@ wgrad_kx_kernel(const KxArgs p)
   uint64_t* empty = bars + 2;       // [2]
   uint64_t* acc_full = bars + 4;
   uint32_t* tmem_base_sh = reinterpret_cast<uint32_t*>(bars + 5);
+  float* xparams = reinterpret_cast<float*>(bars + 16);
+  float* gparams = xparams + 5 * p.cin_p;
+  fillns::stage_params(p.x, xparams, p.cin_p, threadIdx.x, kThreads);
+  fillns::stage_params(p.g, gparams, p.cout_p, threadIdx.x, kThreads);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int group = blockIdx.y, slab = blockIdx.x;
@@ -133,10 +137,10 @@ wgrad_kx_kernel(const KxArgs p)
       uint8_t* xs = stages + (size_t)st * p.stage_bytes;
       uint8_t* gs = xs + p.x_bytes;
       // X window: rows oy + ky0 - pad ..., columns from ox - pad (zero outside the image)
-      fillns::fill_window<kProducerThreads>(p.x, xs, p.x_plane, x_lo, p.nsplit, n, p.H, p.W, oy + ky0 - p.pad, ox - p.pad, p.x_rows, p.x_cols, 0, p.x_chunks, tid);
+      fillns::fill_window<kProducerThreads>(p.x, xs, p.x_plane, x_lo, p.nsplit, n, p.H, p.W, oy + ky0 - p.pad, ox - p.pad, p.x_rows, p.x_cols, 0, p.x_chunks, tid, xparams, p.cin_p);
       // G tile: zero outside this tile's own columns [ox, ox + TW); as the N operand it is stored with k-1 zero
       // columns in front so that N-group j (start + j pixels) is the tile shifted by kx = k-1-j
-      fillns::fill_window<kProducerThreads>(p.g, gs, p.g_plane, g_lo, p.nsplit, n, p.H, p.W, oy, p.n_is_g ? ox - (p.k - 1) : ox, p.TH, p.g_cols, 0, p.g_chunks, tid,
+      fillns::fill_window<kProducerThreads>(p.g, gs, p.g_plane, g_lo, p.nsplit, n, p.H, p.W, oy, p.n_is_g ? ox - (p.k - 1) : ox, p.TH, p.g_cols, 0, p.g_chunks, tid, gparams, p.cout_p,
                           ox, ox + p.TW);
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&full[st]);
@@ -200,6 +204,7 @@ int cvd_conv_wgrad_kx(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oi
   p.dw = dw_oihw; p.N = N; p.H = H; p.W = W; p.k = k; p.pad = (k - 1) / 2;
   p.cin_w = cin; p.cout_w = cout; p.nsplit = precision;
   const int cin_p = round_up(cin, 8), cout_p = round_up(cout, 8);
+  p.cin_p = cin_p; p.cout_p = cout_p;
   p.n_is_g = cin_p >= cout_p;
   const int cm = p.n_is_g ? cin_p : cout_p, cn = p.n_is_g ? cout_p : cin_p;
   if (cm > 128) return 2;
@@ -213,7 +218,7 @@ int cvd_conv_wgrad_kx(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oi
   p.x_chunks = cin_p / 8; p.g_chunks = cout_p / 8;
   const int m_chunks_read = p.Mrows / 8;                       // the M descriptor always walks Mrows/8 planes
   const int max_ky_span = (p.acc_per_cta + p.ncn - 2) / p.ncn + 1;
-  const int budget = 200 * 1024;
+  const int budget = 218 * 1024;
   bool found = false;
   const int tws[3] = {64, 32, 16};
   const int force_tw = getenv("CVD_KX_TW") ? atoi(getenv("CVD_KX_TW")) : 0;      // tuning overrides
@@ -233,7 +238,7 @@ int cvd_conv_wgrad_kx(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oi
       const int gch = !p.n_is_g ? (m_chunks_read > p.g_chunks ? m_chunks_read : p.g_chunks) : p.g_chunks;
       // the shifted N views run up to (k-1)*16 + 15*16 bytes past the last K step of a row: keep one spare plane row
       const int xb = xpl * xch * (precision == 3 ? 2 : 1) + 512, gb = gpl * gch * (precision == 3 ? 2 : 1) + 512;
-      if (2 * (round_up(xb, 128) + round_up(gb, 128)) + 1024 > budget) continue;
+      if (2 * (round_up(xb, 128) + round_up(gb, 128)) + 1024 + fillns::param_bytes(cin_p + cout_p) > budget) continue;
       p.TW = TW; p.TH = th; p.ksteps = kcols / 16;
       p.x_rows = x_rows; p.x_cols = x_cols; p.x_plane = xpl; p.g_cols = g_cols; p.g_plane = gpl;
       p.x_bytes = round_up(xb, 128); p.g_bytes = round_up(gb, 128);
@@ -251,7 +256,7 @@ int cvd_conv_wgrad_kx(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oi
   int cols = p.acc_per_cta * p.NC, pw = 32;
   while (pw < cols) pw <<= 1;
   p.tmem_cols = pw;
-  const size_t smem = (size_t)p.nstages * p.stage_bytes + 1024;
+  const size_t smem = (size_t)p.nstages * p.stage_bytes + 1024 + fillns::param_bytes(p.cin_p + p.cout_p);
   cudaError_t e = cudaSuccess;
 #define CVD_KX_LAUNCH(NS)                                                                                      \
   do {                                                                                                         \

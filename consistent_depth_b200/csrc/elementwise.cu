@@ -395,7 +395,7 @@ extern "C" int cvd_bn_stats(const float* x, int c_total, int c_off, int C, long 
   CVD_CHECK_ARG(C > 0 && C <= 256 && (C & 3) == 0 && (c_off & 3) == 0 && (c_total & 3) == 0 && npix > 0,
                 "cvd_bn_stats: bad channels C=%d c_off=%d c_total=%d", C, c_off, c_total);
   const int lanes = 256 / (C >> 2);
-  long long blocks = (npix + lanes * 64 - 1) / ((long long)lanes * 64);
+  long long blocks = (npix + lanes * 16 - 1) / ((long long)lanes * 16);   // small tensors: spread over the SMs
   const long long cap = (long long)cvd_num_sms() * 2;       // few blocks: the f64 atomics per block are the tail cost
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
@@ -416,7 +416,7 @@ extern "C" int cvd_bn_bwd_reduce(const float* x, int x_ctotal, int x_coff,
   CVD_CHECK_ARG(C > 0 && C <= 256 && (C & 3) == 0 && (x_coff & 3) == 0 && (x_ctotal & 3) == 0 && (dy_ctotal & 3) == 0,
                 "cvd_bn_bwd_reduce: bad channels");
   const int lanes = 256 / (C >> 2);
-  long long blocks = (npix + lanes * 64 - 1) / ((long long)lanes * 64);
+  long long blocks = (npix + lanes * 16 - 1) / ((long long)lanes * 16);
   const long long cap = (long long)cvd_num_sms() * 3;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
