@@ -113,6 +113,7 @@ class FineTuneStep:
             with torch.cuda.graph(self.graph):
                 self._body_single()
         self.graph.replay()
+        self.model.P.num_batches_tracked += 1          # the replayed forward ran in train mode (BN momentum update)
         return self.loss
 
     def _snapshot_and_restore(self, fn):
@@ -139,6 +140,7 @@ class FineTuneStep:
                 self._fwd_bwd()
         if self.use_graph:
             self.graph.replay()
+            P.num_batches_tracked += 1
         else:
             self._fwd_bwd()
         # ONE all-reduce over NVLink: [flat gradient | local loss (already divided by B_global)], in place

@@ -1,0 +1,66 @@
+"""GPU: the DepthFineTuner drop-in end to end on a tiny synthetic clip written in the reference's on-disk layout:
+dataset files -> VideoDataset -> fine_tune() (validation passes, fused CUDA-graph steps, checkpoints) -> save_depth().
+Checks the boundary contract of depth_fine_tuning.py:139-406 (attributes, files written, checkpoint keys)."""
+import json
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def make_params(root, **kw):
+    p = types.SimpleNamespace(path=root, model_type="mc", batch_size=2, learning_rate=0, optimizer="Adam", num_epochs=2,
+                              lambda_view_baseline=-1, lambda_reprojection=1.0, lambda_parameter=0, val_epoch_freq=1,
+                              print_freq=1, display_freq=100, save_epoch_freq=1, log_dir=None)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def test_fine_tune_and_save_depth_end_to_end(tmp_path):
+    from consistent_depth_b200.depth_fine_tuning import DepthFineTuner, make_tag
+    from consistent_depth_b200.monodepth import mc_arch
+    from consistent_depth_b200.synthetic_dataset import write_synthetic_dataset
+    from consistent_depth_b200.utils import image_io
+    root, range_dir = str(tmp_path / "clip"), str(tmp_path / "clip" / "R0-4_hierarchical2_mc")
+    H, W, n = 32, 48, 4
+    write_synthetic_dataset(root, range_dir, n, H, W, pairs=[(0, 1), (1, 2), (2, 3), (0, 2)])
+    params = make_params(root)
+    ft = DepthFineTuner(range_dir, list(range(n)), params)
+    # params.py:110-119 semantics: sentinels resolved from the model class
+    assert params.learning_rate == 0.0004 and params.lambda_view_baseline == 0.1
+    assert ft.out_dir == os.path.join(range_dir, make_tag(params)) and os.path.isdir(os.path.join(ft.out_dir, "checkpoints"))
+    w0 = ft.model.P.flat.clone()
+    ft.save_depth(os.path.join(range_dir, "depth_mc"), list(range(n)))            # initial depth (eval mode)
+    d0 = image_io.load_raw_float32_image(os.path.join(range_dir, "depth_mc", "depth", "frame_000002.raw"))
+    assert d0.shape == (H, W) and np.isfinite(d0).all() and (d0 > 0).all()
+    ft.fine_tune(writer=None)
+    assert (ft.model.P.flat - w0).abs().max().item() > 0                            # weights moved
+    for e in (1, 2):
+        ck = torch.load(os.path.join(ft.out_dir, "checkpoints", f"{e:04d}.pth"), map_location="cpu")
+        assert list(ck.keys()) == list(mc_arch.state_dict_shapes().keys())           # reference state_dict keys / order
+    ev = os.path.join(ft.out_dir, "eval")
+    losses = json.load(open(os.path.join(ev, "loss_e0002_iter000008.json")))
+    assert set(losses) == {"reprojection", "disparity", "mean"} and len(losses["reprojection"]) == 4
+    assert os.path.isfile(os.path.join(ev, "depth_000003_e0000_iter000000.raw"))
+    ft.save_depth()                                                                   # final depth export
+    d1 = image_io.load_raw_float32_image(os.path.join(ft.out_dir, "depth", "frame_000002.raw"))
+    assert d1.shape == (H, W) and np.isfinite(d1).all()
+    # BN running statistics were updated by training AND by the train-mode validation passes
+    assert ft.model.P.num_batches_tracked > 8
+
+
+def test_registry_surface():
+    from consistent_depth_b200.monodepth.depth_model_registry import get_depth_model, get_depth_model_list
+    from consistent_depth_b200.monodepth.mannequin_challenge_model import MannequinChallengeModel
+    assert get_depth_model_list() == ["mc", "midas2", "monodepth2"]
+    assert get_depth_model("mc") is MannequinChallengeModel
+    assert (MannequinChallengeModel.align, MannequinChallengeModel.learning_rate, MannequinChallengeModel.lambda_view_baseline) == (16, 0.0004, 0.1)
+    with pytest.raises(ValueError):
+        get_depth_model("nope")
+    with pytest.raises(NotImplementedError):
+        get_depth_model("midas2")
