@@ -51,14 +51,16 @@ __device__ __forceinline__ void fill_window_impl(const SrcView& s, uint8_t* dst,
   const int total = rows * cols * nchunks;
   const size_t img_off = (size_t)n * H * W;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int base = tid; base < total; base += kProducers * UNROLL) {
+  // item -> (chunk c8, window pixel hp -> (r, c)) is tracked incrementally: one division pair per call, none per item
+  const int dch = kProducers % nchunks, dhp = kProducers / nchunks;
+  int it = tid;
+  int c8 = it % nchunks, hp = it / nchunks;
+  int r = hp / cols, c = hp - r * cols;
+  for (; it < total; ) {
     float4 xa[UNROLL], xb[UNROLL], da[UNROLL], db[UNROLL];
     int hps[UNROLL], c8s[UNROLL]; bool ok[UNROLL], sec[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      const int it = base + u * kProducers;
-      const int c8 = it % nchunks, hp = it / nchunks;
-      const int r = hp / cols, c = hp - r * cols;
       hps[u] = it < total ? hp : -1; c8s[u] = c8;
       const int cl = cfirst + c8 * 8;
       const int iy = y0 + r, ix = x0 + c;
@@ -76,6 +78,11 @@ __device__ __forceinline__ void fill_window_impl(const SrcView& s, uint8_t* dst,
           if (sec[u]) db[u] = __ldg(reinterpret_cast<const float4*>(dp + 4));
         }
       }
+      // advance to this thread's next item
+      it += kProducers; c8 += dch; int adv = dhp;
+      if (c8 >= nchunks) { c8 -= nchunks; ++adv; }
+      hp += adv; c += adv;
+      while (c >= cols) { c -= cols; ++r; }
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
@@ -84,10 +91,14 @@ __device__ __forceinline__ void fill_window_impl(const SrcView& s, uint8_t* dst,
       if (ok[u]) {
         const float xv[8] = {xa[u].x, xa[u].y, xa[u].z, xa[u].w, xb[u].x, xb[u].y, xb[u].z, xb[u].w};
         const int cl = cfirst + c8s[u] * 8;
+        const float4 a0 = *reinterpret_cast<const float4*>(sp + cl), a1 = *reinterpret_cast<const float4*>(sp + cl + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(sp + nch + cl), b1 = *reinterpret_cast<const float4*>(sp + nch + cl + 4);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         if (MODE == CVD_XF_AFFINE) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float t = fmaf(sp[cl + i], xv[i], sp[nch + cl + i]);
+            const float t = fmaf(av[i], xv[i], bv[i]);
             v[i] = s.relu ? fmaxf(t, 0.f) : t;
           }
         } else {
@@ -95,7 +106,7 @@ __device__ __forceinline__ void fill_window_impl(const SrcView& s, uint8_t* dst,
           const float dv[8] = {da[u].x, da[u].y, da[u].z, da[u].w, db[u].x, db[u].y, db[u].z, db[u].w};
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float y = fmaf(sp[cl + i], xv[i], sp[nch + cl + i]);
+            const float y = fmaf(av[i], xv[i], bv[i]);
             const float gq = (!s.relu || y > 0.f) ? dv[i] : 0.f;
             v[i] = sp[2 * nch + cl + i] * gq - sp[3 * nch + cl + i] - sp[4 * nch + cl + i] * y;
           }

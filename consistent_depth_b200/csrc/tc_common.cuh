@@ -144,14 +144,16 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn_major, 
 // v ~= hi + lo with hi = bf16(v), lo = bf16(v - hi): 16+ significant bits; the products
 // Ahi*Bhi + Alo*Bhi + Ahi*Blo (fp32 accumulate) give fp32-class accuracy on bf16 tensor cores.
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  // packed conversions: cvt.rn.bf16x2.f32 takes two floats; a bf16 widened back to fp32 is a 16-bit shift / mask
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-    __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
-    __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    uint32_t hp;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hp) : "f"(v[2 * i + 1]), "f"(v[2 * i]));   // low half <- v[2i]
+    const float h0 = __uint_as_float(hp << 16), h1 = __uint_as_float(hp & 0xffff0000u);
+    uint32_t lp;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lp) : "f"(v[2 * i + 1] - h1), "f"(v[2 * i] - h0));
+    h[i] = hp; l[i] = lp;
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
