@@ -173,6 +173,9 @@ class McEngine:
         self.P = params
         self.N, self.H, self.W, self.dev, self.prec = n_frames, H, W, params.dev, precision
         self.train_mode = True
+        import os
+        self.multi_stream = os.environ.get("CVD_MULTI_STREAM", "1") == "1"
+        self.side_streams = []
         self.pmap, self.grad_flat = params.pmap, params.grad_flat
         self._p, self._g, self._rb = params._p, params._g, params._rb
         self._build_plan()
@@ -264,14 +267,19 @@ class McEngine:
         self._stats(one, 0, o0 + A, N * h * w, f"{prefix}.convs.0.1.running_mean", f"{prefix}.convs.0.1.running_var")
         mids, outs = [], []
         aoff, boff = o0, o0 + A
-        for i in range(3):
+        main_list, branches = self.fwd, []
+        for i in range(3):                                     # the three k x k convs are independent: parallel branches
             mid = sub(aoff, As[i])
+            self.fwd = []
             self._conv(mid, f"{prefix}.convs.{i + 1}.3.weight", f"{prefix}.convs.{i + 1}.3.bias", _T(buf, off=boff),
                        As[i], Bs[i], ks[i], N, h, w)
+            branches.append(self.fwd)
             mids.append(mid)
             outs.append(sub(boff, Bs[i]))
             aoff += As[i]
             boff += Bs[i]
+        self.fwd = main_list
+        self.fwd.append(("par", branches))
         kout = sub(o0 + A, Bt)
         self._stats(kout, o0 + A, Bt, N * h * w, f"{prefix}.convs.1.4.running_mean", f"{prefix}.convs.1.4.running_var")
         out = _T(buf, off=0, n0=o0, gap=A, C=o0 + Bt, a=a, b=b, relu=True, dbuf=dbuf)
@@ -362,7 +370,9 @@ class McEngine:
                 dbk = self.grad_flat[self.pmap[f"{prefix}.convs.1.3.bias"][0]:][:Bt]
                 self.bwd.append(lambda buf=buf, dbuf=dbuf, a=a, b=b, rstd=rstd, mean=mean, bw=bw, dbk=dbk, lo=o0 + A, cnt=Bt, npix=npix:
                                 ops.bn_bwd_reduce(buf, lo, cnt, dbuf, npix, scratch, a, b, rstd, mean, bw, True, dbias=dbk))
+                kbranches = []
                 for i in range(3):
+                    main_bwd, self.bwd = self.bwd, []
                     Wt = self._p(f"{prefix}.convs.{i + 1}.3.weight")
                     pkt = self._packed(Bs[i], As[i], ks[i])
                     self.pack_bwd.append((Wt, pkt, True))
@@ -373,6 +383,10 @@ class McEngine:
                     d = ops.make_dst(mids[i].dview())
                     self.bwd.append(lambda gs=gs, pkt=pkt, d=d, ci=Bs[i], co=As[i], k=ks[i], h=h, w=w:
                                     ops.conv(gs, pkt, None, d, N, h, w, ci, co, k, prec, 0))
+                    kbranches.append([[self.bwd[0]], [self.bwd[1]]])
+                    self.bwd = main_bwd
+                # wgrad and dgrad of each of the three convs: six independent kernels
+                self.bwd.append(("par", [b for pair in kbranches for b in pair]))
                 db1 = self.grad_flat[self.pmap[f"{prefix}.convs.0.0.bias"][0]:][:o0 + A]
                 self.bwd.append(lambda buf=buf, dbuf=dbuf, a=a, b=b, rstd=rstd, mean=mean, bw=bw, db1=db1, cnt=o0 + A, npix=npix:
                                 ops.bn_bwd_reduce(buf, 0, cnt, dbuf, npix, scratch, a, b, rstd, mean, bw, True, dbias=db1))
@@ -380,16 +394,19 @@ class McEngine:
                 W1 = self._p(f"{prefix}.convs.0.0.weight", shape=(o0 + A, cin, 1, 1))
                 dW1 = self._g(f"{prefix}.convs.0.0.weight", shape=(o0 + A, cin, 1, 1))
                 gs, xs = one.bnbwd_src(), x.src()
-                self.bwd.append(lambda gs=gs, xs=xs, dW1=dW1, cin=cin, co=o0 + A, h=h, w=w:
-                                ops.conv_wgrad(gs, xs, dW1, N, h, w, cin, co, 1, prec))
+                wg = (lambda gs=gs, xs=xs, dW1=dW1, cin=cin, co=o0 + A, h=h, w=w:
+                      ops.conv_wgrad(gs, xs, dW1, N, h, w, cin, co, 1, prec))
                 if x.dbuf is not None:
                     pkt = self._packed(o0 + A, cin, 1)
                     self.pack_bwd.append((W1, pkt, True))
                     d = ops.make_dst(x.dview())
                     fl = ops.FLAG_ACCUM if x.grad_written else 0
-                    self.bwd.append(lambda gs=gs, pkt=pkt, d=d, fl=fl, ci=o0 + A, co=cin, h=h, w=w:
-                                    ops.conv(gs, pkt, None, d, N, h, w, ci, co, 1, prec, fl))
+                    dg = (lambda gs=gs, pkt=pkt, d=d, fl=fl, ci=o0 + A, co=cin, h=h, w=w:
+                          ops.conv(gs, pkt, None, d, N, h, w, ci, co, 1, prec, fl))
+                    self.bwd.append(("par", [[wg], [dg]]))
                     x.grad_written = True
+                else:
+                    self.bwd.append(wg)
             elif kind == "conv1":
                 _, img, t0 = rec
                 H, W = self.H, self.W
@@ -402,13 +419,40 @@ class McEngine:
                 self.bwd.append(lambda gs=gs, xs=xs, dW=dW: ops.conv_wgrad(gs, xs, dW, N, H, W, 3, 128, 7, prec))
 
     # ------------------------------------------------------------------ execution
+    def _run(self, plan):
+        """Plan entries are callables (serial, current stream) or ("par", [branch, ...]): independent branches
+        forked onto side streams and joined back — inside the CUDA graph they become parallel branches, which
+        keeps the SMs busy on the low-resolution hourglass levels whose kernels have fewer CTAs than the GPU has SMs."""
+        main = torch.cuda.current_stream()
+        for op in plan:
+            if not isinstance(op, tuple):
+                op()
+                continue
+            branches = op[1]
+            if not self.multi_stream or len(branches) == 1:
+                for br in branches:
+                    for f in br:
+                        f()
+                continue
+            while len(self.side_streams) < len(branches) - 1:
+                self.side_streams.append(torch.cuda.Stream(device=self.dev))
+            for f in branches[0]:
+                f()
+            for i, br in enumerate(branches[1:]):
+                s = self.side_streams[i]
+                s.wait_stream(main)
+                with torch.cuda.stream(s):
+                    for f in br:
+                        f()
+            for i in range(len(branches) - 1):
+                main.wait_stream(self.side_streams[i])
+
     def forward(self, images):
         """images (N,3,H,W) BGR in [0,1] (CUDA, contiguous) -> depth (N,H,W) (engine-owned buffer)."""
         assert images.shape == (self.N, 3, self.H, self.W), images.shape
         ops.image_to_nhwc4(images.contiguous(), self.img4, self.N, self.H, self.W)
         ops.pack_batch(self.pack_fwd_tab[0], self.pack_fwd_tab[1], self.prec)
-        for f in self.fwd:
-            f()
+        self._run(self.fwd)
         if self.train_mode:
             self.P.num_batches_tracked += 1
         return self.depth.view(self.N, self.H, self.W)
@@ -417,5 +461,4 @@ class McEngine:
         """grad_depth (N,H,W): d loss / d depth.  Accumulates into grad_flat (zero it first, as opt.zero_grad does)."""
         self.grad_depth = grad_depth.contiguous()
         ops.pack_batch(self.pack_bwd_tab[0], self.pack_bwd_tab[1], self.prec)
-        for f in self.bwd:
-            f()
+        self._run(self.bwd)
