@@ -30,6 +30,13 @@ class cvd_dst_t(C.Structure):
     _fields_ = [("y", C.c_void_p), ("c_total", C.c_int), ("c_off", C.c_int), ("n0", C.c_int), ("gap", C.c_int)]
 
 
+class cvd_bn_t(C.Structure):
+    _fields_ = [("scratch", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
+                ("a", C.c_void_p), ("b", C.c_void_p), ("rstd", C.c_void_p), ("mean", C.c_void_p),
+                ("eps", C.c_float), ("momentum", C.c_float)]
+
+
 _lib = None
 
 

@@ -58,6 +58,9 @@ struct ConvArgs {
   int ntiles;
   int stage_bytes, nstages, kbs, kb_bytes;    // a weight stage = kbs k-blocks of kb_bytes each
   int tmem_cols;
+  // fused BatchNorm(train) statistics of the conv output (NULL scratch: off)
+  double* st_scratch; const float* st_gamma; const float* st_beta; float* st_rm; float* st_rv;
+  float* st_a; float* st_b; float* st_rstd; float* st_mean; float st_eps, st_mom; long long st_count;
 };
 
 __device__ __forceinline__ int view_phys(int c, int c0, int n0, int gap) { return c0 + c + (c >= n0 ? gap : 0); }
@@ -81,6 +84,8 @@ conv_tc_kernel(const ConvArgs p)
   uint32_t* tmem_base_sh = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* sparams = reinterpret_cast<float*>(bars + 32);           // per-channel constants, 5 x cin floats
   fillns::stage_params(p.src, sparams, p.cin, threadIdx.x, kThreads);
+  float* sstat = sparams + 5 * p.cin;                              // [4 epilogue warps][2][cout] column sums / sums of squares
+  if (p.st_scratch) for (int i = threadIdx.x; i < 8 * p.cout; i += kThreads) sstat[i] = 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -102,12 +107,10 @@ conv_tc_kernel(const ConvArgs p)
   const uint32_t tmem_base = *tmem_base_sh;
 
   const int taps = p.k * p.k;
-  const int kb_full = (p.ngroups == 1 ? p.cin : kGroupCh * 1) >> 4;   // placeholder, recomputed per item below
 
   // item i of a tile -> (pack group g64, sub-group h): channel range and k-block range inside the pack group
   auto item_cfirst = [&](int it) { return p.gsplit == 2 ? (it >> 1) * kGroupCh + (it & 1) * 32 : it * kGroupCh; };
   auto item_chunks = [&](int it) { return p.gsplit == 2 ? 4 : min(p.gchunks, (p.cin - it * kGroupCh) >> 3); };
-  (void)kb_full;
 
   if (warp < kIssuers) {
     // ============================ MMA issuers ============================
@@ -247,11 +250,40 @@ conv_tc_kernel(const ConvArgs p)
         for (int c16 = 0; c16 < p.cout; c16 += 16) {
           float v[16];
           tc::tmem_ld16(taddr + (uint32_t)c16, v);    // warp-collective: executed by all lanes
-          if (!inside || c16 >= p.cout_valid) continue;
           if (p.bias) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) if (c16 + i < p.cout_valid) v[i] += __ldg(p.bias + c16 + i);
           }
+          if (p.st_scratch) {
+            // BatchNorm batch statistics fused into the epilogue: column sums over the warp's 32 pixels by a
+            // transposing butterfly (8+4+2+1+1 shuffles per quantity), accumulated per warp in shared memory.
+            float sv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sv[i] = inside ? v[i] : 0.f;
+            float tot[2];
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq) {
+              float t8[8], t4[4], t2[2];
+              const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float lo_ = qq ? sv[i] * sv[i] : sv[i], hi_ = qq ? sv[8 + i] * sv[8 + i] : sv[8 + i];
+                t8[i] = (b4 ? hi_ : lo_) + __shfl_xor_sync(0xffffffffu, b4 ? lo_ : hi_, 16);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) t4[i] = (b3 ? t8[4 + i] : t8[i]) + __shfl_xor_sync(0xffffffffu, b3 ? t8[i] : t8[4 + i], 8);
+#pragma unroll
+              for (int i = 0; i < 2; ++i) t2[i] = (b2 ? t4[2 + i] : t4[i]) + __shfl_xor_sync(0xffffffffu, b2 ? t4[i] : t4[2 + i], 4);
+              const float t1 = (b1 ? t2[1] : t2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? t2[0] : t2[1], 2);
+              tot[qq] = t1 + __shfl_xor_sync(0xffffffffu, t1, 1);
+            }
+            if (!(lane & 1)) {                           // 16 lanes hold the 16 distinct columns of this chunk
+              const int col = c16 + ((lane >> 1) & 1) + ((lane >> 2) & 1) * 2 + ((lane >> 3) & 1) * 4 + ((lane >> 4) & 1) * 8;
+              float* ws = sstat + (size_t)q * 2 * p.cout;
+              ws[col] += tot[0]; ws[p.cout + col] += tot[1];
+            }
+          }
+          if (!inside || c16 >= p.cout_valid) continue;
           if (do_exp) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = expf(v[i]);
@@ -272,6 +304,47 @@ conv_tc_kernel(const ConvArgs p)
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);   // accumulator buffer free for tile ti + 2
+    }
+    if (p.st_scratch) {
+      // CTA partials -> f64 atomics; the last CTA (ticket) finalises a = gamma*rstd, b = beta - mean*a and the
+      // running statistics exactly as bn_stats_kernel does (hourglass.py:28,40,43,165, train mode)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int et = threadIdx.x - 32 * (kIssuers + 9);
+      for (int c = et; c < p.cout_valid; c += 128) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { s1 += sstat[(size_t)w * 2 * p.cout + c]; s2 += sstat[(size_t)w * 2 * p.cout + p.cout + c]; }
+        atomicAdd(p.st_scratch + 2 * c, (double)s1);
+        atomicAdd(p.st_scratch + 2 * c + 1, (double)s2);
+      }
+      __threadfence();
+      volatile int& last_cta = *reinterpret_cast<volatile int*>(tmem_base_sh + 1);   // (static smem would exceed the 227 KB opt-in)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(p.st_scratch + 2 * 256);
+        last_cta = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+        if (last_cta) *ticket = 0u;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (last_cta) {
+        __threadfence();
+        for (int c = et; c < p.cout_valid; c += 128) {
+          const double sum = __ldcg(p.st_scratch + 2 * c), sq = __ldcg(p.st_scratch + 2 * c + 1);
+          p.st_scratch[2 * c] = 0.0; p.st_scratch[2 * c + 1] = 0.0;
+          const double mean = sum / (double)p.st_count;
+          double var = sq / (double)p.st_count - mean * mean;
+          if (var < 0.0) var = 0.0;
+          const float rs = (float)(1.0 / sqrt(var + (double)p.st_eps));
+          const float g = p.st_gamma ? p.st_gamma[c] : 1.f, be = p.st_beta ? p.st_beta[c] : 0.f;
+          const float av = g * rs;
+          p.st_a[c] = av; p.st_b[c] = be - (float)mean * av; p.st_rstd[c] = rs; p.st_mean[c] = (float)mean;
+          if (p.st_rm) {
+            const double unb = p.st_count > 1 ? var * (double)p.st_count / (double)(p.st_count - 1) : var;
+            p.st_rm[c] = (1.f - p.st_mom) * p.st_rm[c] + p.st_mom * (float)mean;
+            p.st_rv[c] = (1.f - p.st_mom) * p.st_rv[c] + p.st_mom * (float)unb;
+          }
+        }
+      }
     }
   }
 
@@ -370,9 +443,9 @@ extern "C" int cvd_conv_pack_batch(const void* descs_dev, int n, int precision, 
   return 0;
 }
 
-extern "C" int cvd_conv_fwd(const cvd_src_t* src, const void* packed_w, const float* bias,
-                            const cvd_dst_t* dst, int N, int H, int W, int cin, int cout, int k,
-                            int precision, int flags, void* stream)
+static int conv_fwd_impl(const cvd_src_t* src, const void* packed_w, const float* bias,
+                         const cvd_dst_t* dst, int N, int H, int W, int cin, int cout, int k,
+                         int precision, int flags, const cvd_bn_t* bn, void* stream)
 {
   CVD_CHECK_ARG(src && dst && packed_w && src->x && dst->y, "cvd_conv_fwd: null pointer");
   CVD_CHECK_ARG(precision == 1 || precision == 3, "cvd_conv_fwd: precision must be 1 (bf16) or 3 (bf16x3)");
@@ -393,6 +466,13 @@ extern "C" int cvd_conv_fwd(const cvd_src_t* src, const void* packed_w, const fl
   p.wp = (const uint8_t*)packed_w; p.bias = bias;
   p.y = dst->y; p.y_ct = dst->c_total; p.y_c0 = dst->c_off; p.y_n0 = dst->n0 > 0 ? dst->n0 : (1 << 30); p.y_gap = dst->gap;
   p.cout_valid = cout;
+  if (bn) {
+    CVD_CHECK_ARG(bn->scratch && bn->a && bn->b && bn->rstd && bn->mean, "cvd_conv_fwd_bn: null pointer");
+    CVD_CHECK_ARG(!(flags & 3), "cvd_conv_fwd_bn: statistics cannot be fused with accumulate / exp");
+    p.st_scratch = (double*)bn->scratch; p.st_gamma = bn->gamma; p.st_beta = bn->beta; p.st_rm = bn->running_mean; p.st_rv = bn->running_var;
+    p.st_a = bn->a + dst->c_off; p.st_b = bn->b + dst->c_off; p.st_rstd = bn->rstd + dst->c_off; p.st_mean = bn->mean + dst->c_off;
+    p.st_eps = bn->eps; p.st_mom = bn->momentum; p.st_count = (long long)N * H * W;
+  }
   p.N = N; p.H = H; p.W = W; p.k = k; p.pad = (k - 1) / 2;
   p.cin = round_up(cin, 16); p.cout = round_up(cout, 16);
   CVD_CHECK_ARG(p.cout <= 256, "cvd_conv_fwd: cout=%d > 256", cout);
@@ -430,7 +510,7 @@ extern "C" int cvd_conv_fwd(const cvd_src_t* src, const void* packed_w, const fl
         const int stage_bytes = kbs * p.kb_bytes;
         const int stages_per_tile = k * k * (p.cin >> 4) / kbs;
         for (int nst = kMaxStages; nst >= 2 && !found; --nst) {
-          if ((size_t)want_slots * slot + (size_t)nst * stage_bytes + 1024 + fillns::param_bytes(p.cin) > (size_t)smem_budget) continue;
+          if ((size_t)want_slots * slot + (size_t)nst * stage_bytes + 1024 + fillns::param_bytes(p.cin) + 32 * p.cout > (size_t)smem_budget) continue;
           p.mtx = mtx; p.mty = mty; p.nslots = want_slots; p.gsplit = gsplit; p.gchunks = gchunks; p.ngroups = items;
           p.HP = HP; p.WP = WP; p.plane_bytes = plane; p.slot_bytes = slot;
           p.kbs = kbs; p.stage_bytes = stage_bytes;
@@ -450,7 +530,7 @@ extern "C" int cvd_conv_fwd(const cvd_src_t* src, const void* packed_w, const fl
   p.tmem_cols = pw;
   CVD_CHECK_ARG(p.plane_bytes < (1 << 18) && p.WP * 16 < (1 << 18), "cvd_conv_fwd: descriptor offset overflow");
 
-  const size_t smem = (size_t)p.nslots * p.slot_bytes + (size_t)p.nstages * p.stage_bytes + 1024 + fillns::param_bytes(p.cin);
+  const size_t smem = (size_t)p.nslots * p.slot_bytes + (size_t)p.nstages * p.stage_bytes + 1024 + fillns::param_bytes(p.cin) + 32 * p.cout;
   const long long grid = p.ntiles < cvd_num_sms() ? p.ntiles : cvd_num_sms();   // persistent: one CTA per SM
   const int MT = p.mtx * p.mty;
   cudaError_t e = cudaSuccess;
@@ -472,4 +552,19 @@ extern "C" int cvd_conv_fwd(const cvd_src_t* src, const void* packed_w, const fl
   if (e != cudaSuccess) return cvd_fail("cvd_conv_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   CVD_LAUNCH_OK("conv_tc_kernel");
   return 0;
+}
+
+extern "C" int cvd_conv_fwd(const cvd_src_t* src, const void* packed_w, const float* bias,
+                            const cvd_dst_t* dst, int N, int H, int W, int cin, int cout, int k,
+                            int precision, int flags, void* stream)
+{
+  return conv_fwd_impl(src, packed_w, bias, dst, N, H, W, cin, cout, k, precision, flags, nullptr, stream);
+}
+
+extern "C" int cvd_conv_fwd_bn(const cvd_src_t* src, const void* packed_w, const float* bias,
+                               const cvd_dst_t* dst, int N, int H, int W, int cin, int cout, int k,
+                               int precision, int flags, const cvd_bn_t* bn, void* stream)
+{
+  CVD_CHECK_ARG(bn != nullptr, "cvd_conv_fwd_bn: bn is NULL");
+  return conv_fwd_impl(src, packed_w, bias, dst, N, H, W, cin, cout, k, precision, flags, bn, stream);
 }

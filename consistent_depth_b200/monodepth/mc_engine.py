@@ -175,6 +175,7 @@ class McEngine:
         self.train_mode = True
         import os
         self.multi_stream = os.environ.get("CVD_MULTI_STREAM", "1") == "1"
+        self.fuse_bn = os.environ.get("CVD_FUSE_BN", "1") == "1"     # BN batch statistics in the conv epilogue
         self.side_streams = []
         self.pmap, self.grad_flat = params.pmap, params.grad_flat
         self._p, self._g, self._rb = params._p, params._g, params._rb
@@ -193,6 +194,7 @@ class McEngine:
         self.raw_outputs = {}
         self.pack_fwd, self.pack_bwd = [], []
         self.scratch = ops.bn_scratch(self.dev)
+        self.conv_scratch = [ops.bn_scratch(self.dev) for _ in range(3)]   # one per concurrently running conv
         self.eval_affine = []            # (a, b, lo, hi, running_mean, running_var, gamma, beta) for eval mode
         self.img4 = self._zeros(N, H, W, 4)
         self.depth = self._zeros(N, H, W, 1)
@@ -203,8 +205,12 @@ class McEngine:
         r0 = self._zeros(N, H, W, 128)
         t0 = _T(r0, C=128, a=self._zeros(128), b=self._zeros(128), relu=True, dbuf=self._zeros(N, H, W, 128))
         t0.rstd, t0.mean, t0.bw = self._zeros(128), self._zeros(128), self._zeros(128, 4)
-        self._conv(img, "seq.0.weight", "seq.0.bias", _T(r0), 3, 128, 7, N, H, W)
-        self._stats(t0, 0, 128, N * H * W, "seq.1.running_mean", "seq.1.running_var", "seq.1.weight", "seq.1.bias")
+        fuse = self.fuse_bn
+        self._conv(img, "seq.0.weight", "seq.0.bias", _T(r0), 3, 128, 7, N, H, W,
+                   bn=(t0, self._rb("seq.1.running_mean", 128), self._rb("seq.1.running_var", 128),
+                       self._p("seq.1.weight"), self._p("seq.1.bias"), 0) if fuse else None)
+        self._stats(t0, 0, 128, N * H * W, "seq.1.running_mean", "seq.1.running_var", "seq.1.weight", "seq.1.bias",
+                    fused=fuse)
         self.recs.append(("conv1", img, t0))
 
         z = self._chan(t0, mc_arch.structure(), "seq.3", H, W)
@@ -217,7 +223,7 @@ class McEngine:
         self.pack_bwd_tab = ops.make_pack_table(self.pack_bwd, self.dev)
 
     # forward helpers ------------------------------------------------------
-    def _conv(self, x, wkey, bkey, dst, cin, cout, k, N, h, w, flags=0, wshape=None):
+    def _conv(self, x, wkey, bkey, dst, cin, cout, k, N, h, w, flags=0, wshape=None, bn=None):
         Wt = self._p(wkey, shape=wshape)
         bias = self._p(bkey, n=cout, shape=(cout,))
         pk = self._packed(cin, cout, k)
@@ -225,10 +231,17 @@ class McEngine:
         self.pack_fwd.append((Wt, pk, False))
         self.raw_outputs[wkey[:-7]] = (dst.buf, dst.off, cout)       # conv prefix -> where its raw output lives
         s, d = x.src(), ops.make_dst(dst.view())
-        self.fwd.append(lambda: ops.conv(s, pk, bias, d, N, h, w, cin, cout, k, prec, flags))
+        bns = None
+        if bn is not None:     # (tensor record, running_mean, running_var, gamma, beta, scratch index): fused batch statistics
+            t, rm, rv, gamma, beta, si = bn
+            bns = ops.make_bn(self.conv_scratch[si], t.a, t.b, t.rstd, t.mean, gamma, beta, rm, rv)
+        self.fwd.append(lambda: ops.conv(s, pk, bias, d, N, h, w, cin, cout, k, prec, flags,
+                                         bn=bns if self.train_mode else None))
         return pk
 
-    def _stats(self, t, lo, cnt, npix, rm_key, rv_key, g_key=None, b_key=None):
+    def _stats(self, t, lo, cnt, npix, rm_key, rv_key, g_key=None, b_key=None, fused=False):
+        """Normalisation constants of channels [lo, lo+cnt) of t.  fused: the producing convs computed the
+        train-mode batch statistics in their epilogues already (cvd_conv_fwd_bn); only eval mode needs work."""
         rm, rv = self._rb(rm_key, cnt), self._rb(rv_key, cnt)
         gamma = self._p(g_key) if g_key else None
         beta = self._p(b_key) if b_key else None
@@ -236,7 +249,8 @@ class McEngine:
 
         def run():
             if self.train_mode:
-                ops.bn_stats(buf, lo, cnt, npix, scratch, a, b, rstd, mean, gamma, beta, rm, rv)
+                if not fused:
+                    ops.bn_stats(buf, lo, cnt, npix, scratch, a, b, rstd, mean, gamma, beta, rm, rv)
             else:                                   # eval(): running statistics (depth_fine_tuning.py:182)
                 av = torch.rsqrt(rv + 1e-5)
                 if gamma is not None:
@@ -262,17 +276,25 @@ class McEngine:
 
         one = sub(0, o0 + A)                                   # fused 1x1 output (o0 | a1 a2 a3)
         cin = x.C
+        fuse = self.fuse_bn
+        rm1 = self._rb(f"{prefix}.convs.0.1.running_mean", o0 + A)
+        rv1 = self._rb(f"{prefix}.convs.0.1.running_var", o0 + A)
         self._conv(x, f"{prefix}.convs.0.0.weight", f"{prefix}.convs.0.0.bias", _T(buf), cin, o0 + A, 1, N, h, w,
-                   wshape=(o0 + A, cin, 1, 1))
-        self._stats(one, 0, o0 + A, N * h * w, f"{prefix}.convs.0.1.running_mean", f"{prefix}.convs.0.1.running_var")
+                   wshape=(o0 + A, cin, 1, 1), bn=(one, rm1, rv1, None, None, 0) if fuse else None)
+        self._stats(one, 0, o0 + A, N * h * w, f"{prefix}.convs.0.1.running_mean", f"{prefix}.convs.0.1.running_var",
+                    fused=fuse)
+        rmk = self._rb(f"{prefix}.convs.1.4.running_mean", Bt)
+        rvk = self._rb(f"{prefix}.convs.1.4.running_var", Bt)
         mids, outs = [], []
         aoff, boff = o0, o0 + A
         main_list, branches = self.fwd, []
         for i in range(3):                                     # the three k x k convs are independent: parallel branches
             mid = sub(aoff, As[i])
             self.fwd = []
+            ko = boff - (o0 + A)
             self._conv(mid, f"{prefix}.convs.{i + 1}.3.weight", f"{prefix}.convs.{i + 1}.3.bias", _T(buf, off=boff),
-                       As[i], Bs[i], ks[i], N, h, w)
+                       As[i], Bs[i], ks[i], N, h, w,
+                       bn=(one, rmk[ko:ko + Bs[i]], rvk[ko:ko + Bs[i]], None, None, i) if fuse else None)
             branches.append(self.fwd)
             mids.append(mid)
             outs.append(sub(boff, Bs[i]))
@@ -281,7 +303,8 @@ class McEngine:
         self.fwd = main_list
         self.fwd.append(("par", branches))
         kout = sub(o0 + A, Bt)
-        self._stats(kout, o0 + A, Bt, N * h * w, f"{prefix}.convs.1.4.running_mean", f"{prefix}.convs.1.4.running_var")
+        self._stats(kout, o0 + A, Bt, N * h * w, f"{prefix}.convs.1.4.running_mean", f"{prefix}.convs.1.4.running_var",
+                    fused=fuse)
         out = _T(buf, off=0, n0=o0, gap=A, C=o0 + Bt, a=a, b=b, relu=True, dbuf=dbuf)
         out.rstd, out.mean, out.bw = rstd, mean, bw
         self.recs.append(("inc", x, prefix, cfg, h, w, one, mids, outs, kout))

@@ -67,8 +67,24 @@ def pack_weights(w_oihw, transpose_flip=False, precision=3, out=None):
     return out
 
 
-def conv(src, packed, bias, dst, N, H, W, cin, cout, k, precision=3, flags=0):
-    """src: cvd_src_t, dst: cvd_dst_t (from make_src/make_dst); cin/cout in GEMM terms."""
+def make_bn(scratch, a, b, rstd, mean, gamma=None, beta=None, running_mean=None, running_var=None, eps=1e-5,
+            momentum=0.1):
+    """cvd_bn_t for conv(..., bn=): a/b/rstd/mean are the destination buffer's per-physical-channel arrays,
+    gamma/beta/running_* this conv's own [cout] arrays."""
+    ts = (scratch, gamma, beta, running_mean, running_var, a, b, rstd, mean)
+    s = _lib.cvd_bn_t(*[_lib.ptr(t).value if t is not None else None for t in ts], eps, momentum)
+    s._keep = ts
+    return s
+
+
+def conv(src, packed, bias, dst, N, H, W, cin, cout, k, precision=3, flags=0, bn=None):
+    """src: cvd_src_t, dst: cvd_dst_t (from make_src/make_dst); cin/cout in GEMM terms.
+    bn (make_bn): also produce the train-mode BatchNorm statistics of the output in the conv epilogue."""
+    if bn is not None:
+        _lib.check(_lib.lib().cvd_conv_fwd_bn(C.byref(src), _lib.ptr(packed), _lib.ptr(bias), C.byref(dst),
+                                              N, H, W, cin, cout, k, precision, flags, C.byref(bn), _lib.stream()),
+                   "cvd_conv_fwd_bn")
+        return
     _lib.check(_lib.lib().cvd_conv_fwd(C.byref(src), _lib.ptr(packed), _lib.ptr(bias), C.byref(dst),
                                        N, H, W, cin, cout, k, precision, flags, _lib.stream()), "cvd_conv_fwd")
 

@@ -155,6 +155,22 @@ int cvd_conv_fwd(const cvd_src_t* src, const void* packed_w, const float* bias,
                  const cvd_dst_t* dst, int N, int H, int W, int cin, int cout, int k,
                  int precision, int flags, void* stream);
 
+/* The same convolution with the BatchNorm2d(train) batch statistics of its OUTPUT fused into the epilogue
+ * (what cvd_bn_stats computes in a separate pass): per-channel sum / sum of squares -> a, b, rstd, mean at
+ * physical channels [dst->c_off, +cout) of the arrays, running statistics of this conv's [cout] arrays updated.
+ * scratch: cvd_bn_scratch_bytes(256) bytes, zeroed once by the caller (self-cleaning; may be shared with
+ * cvd_bn_stats / cvd_bn_bwd_reduce as long as the calls are stream-ordered). */
+typedef struct {
+  void* scratch;
+  const float* gamma; const float* beta;        /* [cout] or NULL (affine=False) */
+  float* running_mean; float* running_var;      /* [cout] or NULL */
+  float* a; float* b; float* rstd; float* mean; /* per physical channel of the destination buffer */
+  float eps, momentum;
+} cvd_bn_t;
+int cvd_conv_fwd_bn(const cvd_src_t* src, const void* packed_w, const float* bias,
+                    const cvd_dst_t* dst, int N, int H, int W, int cin, int cout, int k,
+                    int precision, int flags, const cvd_bn_t* bn, void* stream);
+
 /* Weight gradient of the same convolution: dW (fp32 OIHW, [cout][cin][k][k]) += sum over all
  * pixels of G (x) X, the wgrad half of autograd's conv backward (depth_fine_tuning.py:282).
  * gsrc: view of the gradient wrt the conv's raw output (CVD_XF_BNBWD of the following BatchNorm,

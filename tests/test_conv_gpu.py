@@ -199,3 +199,50 @@ def test_conv_wgrad_with_transforms_on_load():
     ops.conv_wgrad(gsrc, xsrc, dw, N, H, W, cin, cout, k, 3)
     torch.cuda.synchronize()
     assert (dw.double() - w.grad).abs().max().item() <= 6e-5 * w.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("cin,cout,k,N,H,W,off", [
+    (128, 208, 1, 2, 32, 48, 0),       # fused inception 1x1: statistics of all 208 columns
+    (64, 16, 11, 2, 32, 48, 24),       # k x k conv writing a channel slice at offset 24 of a wider buffer
+    (32, 64, 5, 1, 20, 28, 8),         # ragged tiles: out-of-image accumulator rows must not count
+    (3, 128, 7, 1, 32, 48, 0),         # conv1 with affine gamma / beta
+])
+def test_conv_fused_batchnorm_statistics(cin, cout, k, N, H, W, off):
+    """cvd_conv_fwd_bn == cvd_conv_fwd followed by nn.BatchNorm2d(train) statistics (hourglass.py:28,40,43,165):
+    a = gamma*rstd, b = beta - mean*a, running stats with momentum 0.1 and unbiased variance; scratch self-cleans."""
+    from consistent_depth_b200 import ops
+    x = rnd(70 + cin, (N, cin, H, W))
+    w = rnd(71 + cout, (cout, cin, k, k), -0.1, 0.1)
+    bias = rnd(72, (cout,))
+    gamma, beta = rnd(73, (cout,), 0.5, 1.5), rnd(74, (cout,))
+    ct = cout + off + 8
+    xb = nhwc(x) if cin % 8 == 0 else torch.cat([nhwc(x), torch.zeros(N, H, W, 4 - cin, device=DEV)], -1).contiguous()
+    yb = torch.zeros(N, H, W, ct, device=DEV)
+    a, b, rstd, mean = (torch.full((ct,), 9.0, device=DEV) for _ in range(4))
+    rm, rv = rnd(75, (cout,)), rnd(76, (cout,), 0.5, 2.0)
+    rm0, rv0 = rm.clone(), rv.clone()
+    scratch = ops.bn_scratch(DEV)
+    pk = ops.pack_weights(w, False, 3)
+    bn = ops.make_bn(scratch, a, b, rstd, mean, gamma, beta, rm, rv)
+    for _ in range(2):       # twice: the scratch must come back zeroed
+        ops.conv(ops.make_src(ops.View(xb, 0)), pk, bias, ops.make_dst(ops.View(yb, off)), N, H, W, cin, cout, k, 3, 0, bn=bn)
+    torch.cuda.synchronize()
+    y = yb[..., off:off + cout].double()
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=k // 2).permute(0, 2, 3, 1)
+    assert (y - ref).abs().max() <= 6e-5 * ref.abs().max()
+    m, v = y.mean((0, 1, 2)), y.var((0, 1, 2), unbiased=False)
+    rs = 1.0 / torch.sqrt(v + 1e-5)
+    sl = slice(off, off + cout)
+    assert torch.allclose(mean[sl].double(), m, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(rstd[sl].double(), rs, rtol=2e-5)
+    assert torch.allclose(a[sl].double(), gamma.double() * rs, rtol=2e-5)
+    assert torch.allclose(b[sl].double(), beta.double() - m * gamma.double() * rs, rtol=1e-4, atol=1e-5)
+    assert (a[:off] == 9).all() and (a[off + cout:] == 9).all()          # neighbours untouched
+    n = N * H * W
+    rm_ref, rv_ref = rm0.double(), rv0.double()
+    for _ in range(2):
+        rm_ref = 0.9 * rm_ref + 0.1 * m
+        rv_ref = 0.9 * rv_ref + 0.1 * v * n / (n - 1)
+    assert torch.allclose(rm.double(), rm_ref, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(rv.double(), rv_ref, rtol=2e-5)
+    assert (scratch == 0).all()
