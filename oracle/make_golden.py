@@ -10,6 +10,9 @@ fixtures hold only what the real reference modules produced for them:
   hourglass_small.npz : monodepth/mannequin_challenge/models/hourglass.py HourglassModel(3)
                       forward (train mode) + grads of a consistency loss, BN running stats
   adam.npz          : optimizer.create("Adam", ...) == torch.optim.Adam, 6 steps
+  monodepth2_small.npz: monodepth/monodepth2/networks ResnetEncoder(18) + DepthDecoder driven exactly as
+                      monodepth/monodepth2_model.py:63-89 does (bicubic in, disp0, bicubic out, reciprocal),
+                      train mode, + grads of the consistency loss (lambda_view_baseline = 1), BN running stats
   finetune_steps.npz: depth_fine_tuning.py:261-283 inner loop (model -> zero_grad -> JointLoss ->
                       backward -> step), 3 steps on one pair
 """
@@ -23,7 +26,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
-from oracle import ref_import, synth, hourglass_oracle as ho  # noqa: E402
+from oracle import ref_import, synth, hourglass_oracle as ho, monodepth2_oracle as m2  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
@@ -110,6 +113,60 @@ def gen_hourglass():
     print("hourglass loss", out["loss"], "ngrads", len(names))
 
 
+MONO2_CASE = dict(seed=51, H=24, W=40, feed=(64, 96), pairs=[(0, 1)])
+MONO2_FULL_GRADS = ("encoder.conv1.weight", "encoder.bn1.weight", "encoder.bn1.bias", "encoder.layer1.0.conv1.weight",
+                    "encoder.layer2.0.downsample.0.weight", "encoder.layer2.0.downsample.1.weight",
+                    "encoder.layer4.1.bn2.weight", "encoder.layer4.1.bn2.bias", "decoder.0.conv.conv.bias",
+                    "decoder.7.conv.conv.weight", "decoder.9.conv.conv.weight", "decoder.10.conv.weight",
+                    "decoder.10.conv.bias")
+MONO2_BUFS = ("encoder.bn1.running_mean", "encoder.bn1.running_var", "encoder.layer2.0.downsample.1.running_var",
+              "encoder.layer4.1.bn2.running_mean", "encoder.layer3.0.bn1.running_var")
+
+
+def gen_monodepth2():
+    import warnings
+    warnings.filterwarnings("ignore")
+    from monodepth.monodepth2.networks.resnet_encoder import ResnetEncoder
+    from monodepth.monodepth2.networks.depth_decoder import DepthDecoder
+    c = MONO2_CASE
+    seed, H, W = c["seed"], c["H"], c["W"]
+    sd = m2.mono2_init_state(seed)
+    enc = ResnetEncoder(18, False)
+    dec = DepthDecoder(num_ch_enc=enc.num_ch_enc, scales=range(4))
+    enc.load_state_dict({k: torch.tensor(v) for k, v in sd.items() if k.startswith("encoder.")})
+    dec.load_state_dict({k: torch.tensor(v) for k, v in sd.items() if k.startswith("decoder.")})
+    enc.train(); dec.train()
+    batch = synth.make_pair_batch(seed, c["pairs"], H, W)
+    images = torch.tensor(batch["images"])                                   # (1,2,3,H,W)
+    # the adapter body, monodepth2_model.py:63-89 (the class itself hard-codes CUDA and a download)
+    x = images.reshape(-1, 3, H, W)
+    x = torch.nn.functional.interpolate(x, size=list(c["feed"]), mode="bicubic", align_corners=False)
+    feats = enc(x)
+    disp0 = dec(feats)[("disp", 0)]
+    disp = torch.nn.functional.interpolate(disp0, size=[H, W], mode="bicubic", align_corners=False)
+    depth = disp.reciprocal().reshape(1, 2, H, W)
+    crit = ref_joint_loss(1.0, 1.0, torch.float32)
+    loss, meta = crit(depth, to_metadata(batch, torch.float32))
+    loss.backward()
+    out = {"resized": x.detach().numpy(), "disp0": disp0.detach().numpy(), "depth": depth.detach().numpy(),
+           "loss": loss.detach().numpy(), "feat4": feats[4].detach().numpy(),
+           "feat0_mean": feats[0].detach().mean((0, 2, 3)).numpy()}
+    params = dict(list(enc.named_parameters()) + list(dec.named_parameters()))
+    names, norms = [], []
+    for k, p in params.items():
+        if p.grad is None:
+            continue
+        names.append(k); norms.append(float(p.grad.double().norm()))
+    out["grad_names"] = np.array(names); out["grad_norms"] = np.array(norms)
+    for k in MONO2_FULL_GRADS:
+        out["grad::" + k] = params[k].grad.numpy()
+    st = dict(enc.state_dict())
+    for k in MONO2_BUFS:
+        out["buf::" + k] = st[k].numpy()
+    np.savez_compressed(os.path.join(OUT, "monodepth2_small.npz"), **out)
+    print("monodepth2 loss", out["loss"], "ngrads", len(names), "depth range", float(depth.min()), float(depth.max()))
+
+
 def gen_adam():
     import optimizer
     p0 = synth.normal(31, 1, (1003,), 0.1)
@@ -156,15 +213,18 @@ def gen_finetune():
 
 
 def main():
-    argparse.ArgumentParser(description=__doc__).parse_args()
+    ap = argparse.ArgumentParser(description=__doc__)
+    ap.add_argument("--only", default=None, help="generate one fixture family: consistency|adam|hourglass|finetune|monodepth2")
+    only = ap.parse_args().only
     ref_import.setup()
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     os.makedirs(OUT, exist_ok=True)
-    gen_consistency()
-    gen_adam()
-    gen_hourglass()
-    gen_finetune()
+    gens = {"consistency": gen_consistency, "adam": gen_adam, "hourglass": gen_hourglass, "finetune": gen_finetune,
+            "monodepth2": gen_monodepth2}
+    for name, fn in gens.items():
+        if only is None or only == name:
+            fn()
 
 
 if __name__ == "__main__":
