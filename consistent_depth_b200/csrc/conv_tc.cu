@@ -362,8 +362,10 @@ __device__ __forceinline__ void pack_one(const float* __restrict__ w, int cin_w,
                                          long long first, long long step)
 {
   // logical GEMM dims: K-channels = cin_pad (multiple of 16), N = cout_pad (multiple of 16)
+  // GEMM N above 256 (the tcgen05 / TMEM limit of one launch) is packed as independent 256-column chunks, one
+  // after the other: chunk j is exactly the blob of a conv with N = min(256, cout_pad - 256 j).
   const int taps = k * k;
-  const int stage_bytes = cout_pad * 32 * (nsplit == 3 ? 2 : 1);
+  const int ns2 = nsplit == 3 ? 2 : 1;
   const long long total = (long long)cin_pad * cout_pad * taps;
   for (long long i = first; i < total; i += step) {
     const int c = (int)(i % cin_pad);
@@ -377,16 +379,20 @@ __device__ __forceinline__ void pack_one(const float* __restrict__ w, int cin_w,
       // GEMM "cin" = forward Cout (w dim 0), GEMM "cout" = forward Cin (w dim 1)
       if (c < cout_w && nn < cin_w) v = w[(((size_t)c * cin_w + nn) * k + (k - 1 - ky)) * k + (k - 1 - kx)];
     }
+    const int nj = nn >> 8, nl = nn & 255;
+    const int cp = min(256, cout_pad - (nj << 8));                 // columns of this chunk
+    const int stage_bytes = cp * 32 * ns2;
+    uint8_t* cout_base = out + (size_t)nj * 256 * cin_pad * taps * 2 * ns2;
     const int g = c / kGroupCh, cg = c - g * kGroupCh;
     const int gch = min(kGroupCh, cin_pad - g * kGroupCh);
     const int kbg = gch / 16;
     // stage index: groups before g contribute taps * (their kb count) stages
     const int stage = g * taps * (kGroupCh / 16) + tap * kbg + cg / 16;
     const int kk = cg & 15;
-    const size_t off = (size_t)stage * stage_bytes + (size_t)(nn >> 3) * 256 + (size_t)(kk >> 3) * 128 + (size_t)(nn & 7) * 16 + (size_t)(kk & 7) * 2;
+    const size_t off = (size_t)stage * stage_bytes + (size_t)(nl >> 3) * 256 + (size_t)(kk >> 3) * 128 + (size_t)(nl & 7) * 16 + (size_t)(kk & 7) * 2;
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    *reinterpret_cast<__nv_bfloat16*>(out + off) = h;
-    if (nsplit == 3) *reinterpret_cast<__nv_bfloat16*>(out + off + (size_t)cout_pad * 32) = __float2bfloat16_rn(v - __bfloat162float(h));
+    *reinterpret_cast<__nv_bfloat16*>(cout_base + off) = h;
+    if (nsplit == 3) *reinterpret_cast<__nv_bfloat16*>(cout_base + off + (size_t)cp * 32) = __float2bfloat16_rn(v - __bfloat162float(h));
   }
 }
 
@@ -447,6 +453,28 @@ static int conv_fwd_impl(const cvd_src_t* src, const void* packed_w, const float
                          const cvd_dst_t* dst, int N, int H, int W, int cin, int cout, int k,
                          int precision, int flags, const cvd_bn_t* bn, void* stream)
 {
+  if (cout > 256) {
+    // more output channels than one launch's TMEM accumulator holds: 256-column chunks (see pack_one)
+    CVD_CHECK_ARG(src && dst && packed_w, "cvd_conv_fwd: null pointer");
+    for (int c0 = 0; c0 < cout; c0 += 256) {
+      const int cc = cout - c0 < 256 ? cout - c0 : 256;
+      cvd_dst_t d = *dst;
+      if (d.gap != 0 && c0 >= d.n0) { d.c_off += c0 + d.gap; d.n0 = 0; d.gap = 0; }
+      else { d.c_off += c0; if (d.gap != 0) d.n0 -= c0; }
+      cvd_bn_t b2;
+      if (bn) {
+        b2 = *bn;
+        if (b2.gamma) b2.gamma += c0;
+        if (b2.beta) b2.beta += c0;
+        if (b2.running_mean) { b2.running_mean += c0; b2.running_var += c0; }
+      }
+      const int rc = conv_fwd_impl(src, (const uint8_t*)packed_w + cvd_conv_packed_bytes(cin, c0, k, precision),
+                                   bias ? bias + c0 : nullptr, &d, N, H, W, cin, cc, k, precision, flags,
+                                   bn ? &b2 : nullptr, stream);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   CVD_CHECK_ARG(src && dst && packed_w && src->x && dst->y, "cvd_conv_fwd: null pointer");
   CVD_CHECK_ARG(precision == 1 || precision == 3, "cvd_conv_fwd: precision must be 1 (bf16) or 3 (bf16x3)");
   CVD_CHECK_ARG(k >= 1 && k <= 11 && (k & 1), "cvd_conv_fwd: k=%d unsupported (odd, <= 11)", k);

@@ -32,6 +32,7 @@ struct WgArgs {
   SrcView g, x;
   float* dw;
   int N, H, W, cin, cout, cin_w, cout_w, k, pad;   // cin/cout padded to 16; *_w = real (dW extents)
+  int dw_ci_stride;                                // Cin of the whole dW tensor (>= cin_w when this launch is a chunk)
   int nsplit;
   int x_is_m;                   // 1: M = X channels (Cin), N = G channels (Cout)
   int Mrows, mblk;              // MMA M (64/128), number of M blocks
@@ -170,7 +171,7 @@ wgrad_tc_kernel(const WgArgs p)
             for (int i = 0; i < 16; ++i) {
               const int nn = c16 + i;
               const int ci = p.x_is_m ? m : nn, co = p.x_is_m ? nn : m;
-              if (ci < p.cin_w && co < p.cout_w) atomicAdd(p.dw + ((size_t)co * p.cin_w + ci) * kk + tap, v[i]);
+              if (ci < p.cin_w && co < p.cout_w) atomicAdd(p.dw + ((size_t)co * p.dw_ci_stride + ci) * kk + tap, v[i]);
             }
           }
         }
@@ -198,10 +199,40 @@ SrcView make_view(const cvd_src_t* s, int cvalid) {
 int cvd_conv_wgrad_kx(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oihw,
                       int N, int H, int W, int cin, int cout, int k, int precision, void* stream);   // conv_wgrad_kx.cu
 
+// logical sub-range [s, ...) of a source view (x and dy views alike)
+static void sub_view(int& c_off, int& n0, int& gap, int s)
+{
+  if (gap != 0 && s >= n0) { c_off += s + gap; n0 = 0; gap = 0; }
+  else { c_off += s; if (gap != 0) n0 -= s; }
+}
+
+static int wgrad_impl(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oihw,
+                      int N, int H, int W, int cin, int cout, int k, int precision, int dw_ci_stride, void* stream);
+
 extern "C" int cvd_conv_wgrad(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oihw,
                               int N, int H, int W, int cin, int cout, int k, int precision, void* stream)
 {
   CVD_CHECK_ARG(gsrc && xsrc && dw_oihw && gsrc->x && xsrc->x, "cvd_conv_wgrad: null pointer");
+  if (cin > 256 || cout > 256) {
+    // channel counts above one launch's limits: 256 x 256 blocks of dW, operands read through sub-views
+    for (int co0 = 0; co0 < cout; co0 += 256)
+      for (int ci0 = 0; ci0 < cin; ci0 += 256) {
+        cvd_src_t g = *gsrc, x = *xsrc;
+        sub_view(g.c_off, g.n0, g.gap, co0); sub_view(g.dy_coff, g.dy_n0, g.dy_gap, co0);
+        sub_view(x.c_off, x.n0, x.gap, ci0); sub_view(x.dy_coff, x.dy_n0, x.dy_gap, ci0);
+        const int rc = wgrad_impl(&g, &x, dw_oihw + ((size_t)co0 * cin + ci0) * k * k, N, H, W,
+                                  cin - ci0 < 256 ? cin - ci0 : 256, cout - co0 < 256 ? cout - co0 : 256, k, precision,
+                                  cin, stream);
+        if (rc) return rc;
+      }
+    return 0;
+  }
+  return wgrad_impl(gsrc, xsrc, dw_oihw, N, H, W, cin, cout, k, precision, cin, stream);
+}
+
+static int wgrad_impl(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oihw,
+                      int N, int H, int W, int cin, int cout, int k, int precision, int dw_ci_stride, void* stream)
+{
   CVD_CHECK_ARG(precision == 1 || precision == 3, "cvd_conv_wgrad: precision must be 1 or 3");
   CVD_CHECK_ARG(k >= 1 && k <= 11 && (k & 1), "cvd_conv_wgrad: k=%d unsupported", k);
   // kx-fused variant (conv_wgrad_kx.cu): measured faster only when the shifted operand is a single 8-channel chunk
@@ -210,7 +241,7 @@ extern "C" int cvd_conv_wgrad(const cvd_src_t* gsrc, const cvd_src_t* xsrc, floa
   const char* kxenv = getenv("CVD_WGRAD_KX");
   const bool kx_all = kxenv && kxenv[0] == 'a';
   const int cmin = cin < cout ? cin : cout;
-  if (k >= 3 && !getenv("CVD_WGRAD_PER_TAP") && (kx_all || cmin <= 8)) {
+  if (k >= 3 && dw_ci_stride == cin && !getenv("CVD_WGRAD_PER_TAP") && (kx_all || cmin <= 8)) {
     const int rc = cvd_conv_wgrad_kx(gsrc, xsrc, dw_oihw, N, H, W, cin, cout, k, precision, stream);
     if (rc != 2) return rc;
   }
@@ -218,6 +249,7 @@ extern "C" int cvd_conv_wgrad(const cvd_src_t* gsrc, const cvd_src_t* xsrc, floa
   p.g = make_view(gsrc, round_up(cout, 4)); p.x = make_view(xsrc, round_up(cin, 4));
   p.dw = dw_oihw; p.N = N; p.H = H; p.W = W; p.k = k; p.pad = (k - 1) / 2;
   p.cin_w = cin; p.cout_w = cout; p.cin = round_up(cin, 16); p.cout = round_up(cout, 16);
+  p.dw_ci_stride = dw_ci_stride;
   p.nsplit = precision;
   CVD_CHECK_ARG(p.cin <= 256 && p.cout <= 256, "cvd_conv_wgrad: channel counts above 256 unsupported");
   p.x_is_m = p.cin >= p.cout;

@@ -392,6 +392,16 @@ extern "C" int cvd_bn_stats(const float* x, int c_total, int c_off, int C, long 
                             float* a, float* b, float* rstd, float* mean, void* stream)
 {
   CVD_CHECK_ARG(x && scratch && a && b && rstd && mean, "cvd_bn_stats: null pointer");
+  if (C > 256) {            // 256-channel chunks (the block-level reduction holds 256 channels); scratch is reused in stream order
+    for (int c0 = 0; c0 < C; c0 += 256) {
+      const int rc = cvd_bn_stats(x, c_total, c_off + c0, C - c0 < 256 ? C - c0 : 256, npix, scratch,
+                                  gamma ? gamma + c0 : nullptr, beta ? beta + c0 : nullptr, eps, momentum,
+                                  running_mean ? running_mean + c0 : nullptr, running_var ? running_var + c0 : nullptr,
+                                  a, b, rstd, mean, stream);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   CVD_CHECK_ARG(C > 0 && C <= 256 && (C & 3) == 0 && (c_off & 3) == 0 && (c_total & 3) == 0 && npix > 0,
                 "cvd_bn_stats: bad channels C=%d c_off=%d c_total=%d", C, c_off, c_total);
   const int lanes = 256 / (C >> 2);
@@ -413,6 +423,17 @@ extern "C" int cvd_bn_bwd_reduce(const float* x, int x_ctotal, int x_coff,
                                  float* bw, float* dgamma, float* dbeta, float* dbias, void* stream)
 {
   CVD_CHECK_ARG(x && dy && a && b && rstd && mean && scratch && bw, "cvd_bn_bwd_reduce: null pointer");
+  if (C > 256) {
+    for (int c0 = 0; c0 < C; c0 += 256) {
+      const int rc = cvd_bn_bwd_reduce(x, x_ctotal, x_coff + c0, dy, dy_ctotal, dy_coff, dy_n0, dy_gap, dy_lc0 + c0,
+                                       a, b, rstd, mean, gamma ? gamma + c0 : nullptr, beta ? beta + c0 : nullptr, relu,
+                                       npix, C - c0 < 256 ? C - c0 : 256, scratch, bw,
+                                       dgamma ? dgamma + c0 : nullptr, dbeta ? dbeta + c0 : nullptr,
+                                       dbias ? dbias + c0 : nullptr, stream);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   CVD_CHECK_ARG(C > 0 && C <= 256 && (C & 3) == 0 && (x_coff & 3) == 0 && (x_ctotal & 3) == 0 && (dy_ctotal & 3) == 0,
                 "cvd_bn_bwd_reduce: bad channels");
   const int lanes = 256 / (C >> 2);

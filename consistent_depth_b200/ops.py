@@ -174,3 +174,104 @@ def make_pack_table(entries, device):
 
 def pack_batch(table, n, precision):
     _lib.check(_lib.lib().cvd_conv_pack_batch(_lib.ptr(table), n, precision, _lib.stream()), "cvd_conv_pack_batch")
+
+
+# ---------------------------------------------------------------- monodepth2 passes (include/cvd.h, second half)
+GATHER_IDENTITY, GATHER_ELU, GATHER_AFFINE_RELU = 0, 1, 2
+
+
+def bicubic_image(img, out4, mean=0.45, std=0.225):
+    """img (N,3,H,W) -> out4 (N,oh,ow,4) = (bicubic(img) - mean) / std."""
+    N, _, H, W = img.shape
+    _lib.check(_lib.lib().cvd_bicubic_image_fwd(_lib.ptr(img), N, H, W, _lib.ptr(out4), out4.shape[1], out4.shape[2],
+                                                C.c_float(mean), C.c_float(1.0 / std), _lib.stream()), "cvd_bicubic_image_fwd")
+
+
+def disp_to_depth(disp, depth):
+    N, fh, fw = disp.shape
+    _lib.check(_lib.lib().cvd_disp_to_depth_fwd(_lib.ptr(disp), N, fh, fw, _lib.ptr(depth), depth.shape[-2], depth.shape[-1],
+                                                _lib.stream()), "cvd_disp_to_depth_fwd")
+
+
+def disp_to_depth_bwd(ddepth, depth, ddisp):
+    N, fh, fw = ddisp.shape
+    _lib.check(_lib.lib().cvd_disp_to_depth_bwd(_lib.ptr(ddepth), _lib.ptr(depth), N, fh, fw, depth.shape[-2], depth.shape[-1],
+                                                _lib.ptr(ddisp), _lib.stream()), "cvd_disp_to_depth_bwd")
+
+
+def sigmoid_fwd(raw_padded, disp):
+    N, fh, fw = disp.shape
+    _lib.check(_lib.lib().cvd_sigmoid_fwd(_lib.ptr(raw_padded), raw_padded.shape[-1], N, fh, fw, _lib.ptr(disp), _lib.stream()),
+               "cvd_sigmoid_fwd")
+
+
+def sigmoid_bwd(ddisp, disp, draw_padded):
+    N, fh, fw = disp.shape
+    _lib.check(_lib.lib().cvd_sigmoid_bwd(_lib.ptr(ddisp), _lib.ptr(disp), N, fh, fw, _lib.ptr(draw_padded),
+                                          draw_padded.shape[-1], _lib.stream()), "cvd_sigmoid_bwd")
+
+
+def subsample2(src, dst):
+    N, H, W, Cn = src.shape
+    _lib.check(_lib.lib().cvd_subsample2(_lib.ptr(src), N, H, W, Cn, _lib.ptr(dst), _lib.stream()), "cvd_subsample2")
+
+
+def stuff2(src, dst, accumulate):
+    N, H, W, Cn = dst.shape
+    _lib.check(_lib.lib().cvd_stuff2(_lib.ptr(src), N, H, W, Cn, _lib.ptr(dst), 1 if accumulate else 0, _lib.stream()),
+               "cvd_stuff2")
+
+
+def bnbwd_stuff(x, dy, a, b, bw, relu, dst, stride):
+    N, h, w, Cn = x.shape
+    _lib.check(_lib.lib().cvd_bnbwd_stuff(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(a), _lib.ptr(b), _lib.ptr(bw), 1 if relu else 0,
+                                          N, h, w, Cn, _lib.ptr(dst), dst.shape[1], dst.shape[2], stride, _lib.stream()),
+               "cvd_bnbwd_stuff")
+
+
+def maxpool_fwd(x, a, b, relu, out, argmax):
+    N, H, W, Cn = x.shape
+    _lib.check(_lib.lib().cvd_maxpool3s2_fwd(_lib.ptr(x), _lib.ptr(a), _lib.ptr(b), 1 if relu else 0, N, H, W, Cn,
+                                             _lib.ptr(out), _lib.ptr(argmax), _lib.stream()), "cvd_maxpool3s2_fwd")
+
+
+def maxpool_bwd(dout, argmax, dx, accumulate):
+    N, H, W, Cn = dx.shape
+    _lib.check(_lib.lib().cvd_maxpool3s2_bwd(_lib.ptr(dout), _lib.ptr(argmax), N, H, W, Cn, _lib.ptr(dx),
+                                             1 if accumulate else 0, _lib.stream()), "cvd_maxpool3s2_bwd")
+
+
+def bn_add_relu(y, a, b, res, ra, rb, out):
+    Cn = y.shape[-1]
+    _lib.check(_lib.lib().cvd_bn_add_relu(_lib.ptr(y), _lib.ptr(a), _lib.ptr(b), _lib.ptr(res), _lib.ptr(ra), _lib.ptr(rb),
+                                          C.c_longlong(y.numel() // Cn), Cn, _lib.ptr(out), _lib.stream()), "cvd_bn_add_relu")
+
+
+def relu_bwd_add(dout, out, dres, accumulate):
+    _lib.check(_lib.lib().cvd_relu_bwd_add(_lib.ptr(dout), _lib.ptr(out), _lib.ptr(dres), 1 if accumulate else 0,
+                                           C.c_longlong(dout.numel()), _lib.stream()), "cvd_relu_bwd_add")
+
+
+def gather_pad_fwd(src, s_coff, s_pad, a, b, dst, d_coff, Cn, upsample, mode):
+    """src (N, hs+2*s_pad, ws+2*s_pad, Cs) -> dst (N, (hs<<up)+2, (ws<<up)+2, Cd) channels [d_coff, d_coff+Cn)."""
+    N = src.shape[0]
+    hs, ws = src.shape[1] - 2 * s_pad, src.shape[2] - 2 * s_pad
+    assert dst.shape[1] == (hs << upsample) + 2 and dst.shape[2] == (ws << upsample) + 2, (src.shape, dst.shape)
+    _lib.check(_lib.lib().cvd_gather_pad_fwd(_lib.ptr(src), src.shape[-1], s_coff, s_pad, _lib.ptr(a), _lib.ptr(b),
+                                             _lib.ptr(dst), dst.shape[-1], d_coff, N, hs, ws, Cn, upsample, mode,
+                                             _lib.stream()), "cvd_gather_pad_fwd")
+
+
+def gather_pad_bwd(dpad, p_coff, src, s_coff, s_pad, dsrc, ds_coff, ds_pad, Cn, upsample, mode, accumulate):
+    N = dsrc.shape[0]
+    hs, ws = dsrc.shape[1] - 2 * ds_pad, dsrc.shape[2] - 2 * ds_pad
+    assert dpad.shape[1] == (hs << upsample) + 2 and dpad.shape[2] == (ws << upsample) + 2, (dpad.shape, dsrc.shape)
+    _lib.check(_lib.lib().cvd_gather_pad_bwd(_lib.ptr(dpad), dpad.shape[-1], p_coff, _lib.ptr(src),
+                                             src.shape[-1] if src is not None else 0, s_coff, s_pad, _lib.ptr(dsrc),
+                                             dsrc.shape[-1], ds_coff, ds_pad, N, hs, ws, Cn, upsample, mode,
+                                             1 if accumulate else 0, _lib.stream()), "cvd_gather_pad_bwd")
+
+
+def channel_sum(x, c_off, Cn, out):
+    _lib.check(_lib.lib().cvd_channel_sum(_lib.ptr(x), x.shape[-1], c_off, Cn, C.c_longlong(x.numel() // x.shape[-1]),
+                                          _lib.ptr(out), _lib.stream()), "cvd_channel_sum")

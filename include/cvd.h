@@ -6,7 +6,7 @@
  * has NO FFI of its own; every entry point below replaces a group of ATen ops
  * the reference dispatches from Python.  Each declaration cites the reference
  * interface (file:line under /root/reference) it stands in for.  The Python
- * host layer (consistent_depth_b200/*.py) binds these with ctypes and mirrors
+ * host layer (the consistent_depth_b200 package) binds these with ctypes and mirrors
  * the reference's module / class / argument names.
  *
  * Conventions
@@ -228,6 +228,71 @@ int cvd_image_to_nhwc4(const float* img_nchw, float* out, int N, int H, int W, v
 /* exp() backward of mannequin_challenge_model.py:66: out4[i] = (grad_depth[i]*depth[i], 0, 0, 0);
  * dbias (pred_layer.bias gradient, 1 float, accumulated) may be NULL. */
 int cvd_dlogdepth(const float* grad_depth, const float* depth, float* out4, long long n, float* dbias, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * monodepth2 backbone: the passes around the conv engine.  All tensors NHWC fp32, plain
+ * (channel offset 0) unless a (c_total, c_off) pair is given; C multiples of 4.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* F.interpolate(images, size=feed, mode='bicubic', align_corners=False) (monodepth2_model.py:72-74) fused with
+ * (x - 0.45) / 0.225 (resnet_encoder.py:89): (N,3,H,W) -> (N,oh,ow,4), 4th channel 0. */
+int cvd_bicubic_image_fwd(const float* img_nchw, int N, int H, int W, float* out_nhwc4, int oh, int ow,
+                          float mean, float inv_std, void* stream);
+
+/* depth = 1 / bicubic(disp -> (H,W)) (monodepth2_model.py:79-82); disp (N,fh,fw), depth (N,H,W).
+ * Backward: ddisp (N,fh,fw) = bicubic^T(-ddepth * depth^2); ddisp is zeroed by the call. */
+int cvd_disp_to_depth_fwd(const float* disp, int N, int fh, int fw, float* depth, int H, int W, void* stream);
+int cvd_disp_to_depth_bwd(const float* ddepth, const float* depth, int N, int fh, int fw, int H, int W,
+                          float* ddisp, void* stream);
+
+/* nn.Sigmoid of depth_decoder.py:63 on channel 0 of the dispconv output, which lives on the reflect-padded grid
+ * (N,fh+2,fw+2,c_total); backward writes channel 0 of the interior of draw_padded (border / other channels untouched). */
+int cvd_sigmoid_fwd(const float* raw_padded, int c_total, int N, int fh, int fw, float* disp, void* stream);
+int cvd_sigmoid_bwd(const float* ddisp, const float* disp, int N, int fh, int fw, float* draw_padded, int c_total, void* stream);
+
+/* Stride-2 convolutions of torchvision's resnet18 (conv1, layerN.0.conv1, layerN.0.downsample.0) run as the stride-1
+ * conv at the input resolution followed by picking pixels (2y,2x):  dst (N,ceil(H/2),ceil(W/2),C) = src[:, ::2, ::2].
+ * cvd_stuff2 is its transpose: dst (N,H,W,C) at (2y,2x) (+)= src; other pixels are not touched. */
+int cvd_subsample2(const float* src, int N, int H, int W, int C, float* dst, void* stream);
+int cvd_stuff2(const float* src, int N, int H, int W, int C, float* dst, int accumulate, void* stream);
+
+/* BatchNorm(+ReLU) backward, materialised: dst[(stride*y, stride*x)] = c0 g - c1 - c2 (a x + b), g = dy [relu: * (a x + b > 0)],
+ * with (c0,c1,c2) = bw[c] from cvd_bn_bwd_reduce; x, dy (N,h,w,C); dst (N,H,W,C), pixels off the stride grid untouched. */
+int cvd_bnbwd_stuff(const float* x, const float* dy, const float* a, const float* b, const float* bw, int relu,
+                    int N, int h, int w, int C, float* dst, int H, int W, int stride, void* stream);
+
+/* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (resnet_encoder.py:93) of relu?(a x + b): (N,H,W,C) ->
+ * (N,ceil(H/2),ceil(W/2),C) + arg-max tap (0..8, first maximum in scan order like torch) per output element.
+ * Backward: dx (N,H,W,C) (+)= sum of dout over the windows whose arg-max is this pixel. */
+int cvd_maxpool3s2_fwd(const float* x, const float* a, const float* b, int relu, int N, int H, int W, int C,
+                       float* out, unsigned char* argmax, void* stream);
+int cvd_maxpool3s2_bwd(const float* dout, const unsigned char* argmax, int N, int H, int W, int C, float* dx,
+                       int accumulate, void* stream);
+
+/* torchvision BasicBlock tail: out = relu(a y + b + r'), r' = ra r + rb (downsample branch) or r (ra = rb = NULL).
+ * Backward: dout <- dout * [out > 0] in place; dres (+)= that (dres may be NULL). */
+int cvd_bn_add_relu(const float* y, const float* a, const float* b, const float* res, const float* ra, const float* rb,
+                    long long npix, int C, float* out, void* stream);
+int cvd_relu_bwd_add(float* dout, const float* out, float* dres, int accumulate, long long n, void* stream);
+
+/* Input of a Conv3x3 of monodepth2 (layers.py:121-136): dst[(N, hu+2, wu+2, d_ctotal) at channels d_coff..] =
+ * ReflectionPad2d(1)( T(src) upsampled x2 nearest if `upsample` ), hu = hs << upsample; torch.cat = two calls with
+ * different d_coff.  src is (N, hs + 2 s_pad, ws + 2 s_pad, s_ctotal) read at its interior (s_pad = 1 for a conv output
+ * that itself lives on a padded grid).  T: identity, ELU (layers.py:113), or relu(a x + b) (encoder feature 0).
+ * Backward (transpose, gather form, deterministic): dsrc (own geometry) (+)= T'(src) * sum of dpad over the pre-images;
+ * for CVD_GATHER_AFFINE_RELU T' = 1 (the ReLU / BatchNorm backward happens where dsrc is consumed). */
+#define CVD_GATHER_IDENTITY 0
+#define CVD_GATHER_ELU 1
+#define CVD_GATHER_AFFINE_RELU 2
+int cvd_gather_pad_fwd(const float* src, int s_ctotal, int s_coff, int s_pad, const float* a, const float* b,
+                       float* dst, int d_ctotal, int d_coff, int N, int hs, int ws, int C, int upsample, int mode,
+                       void* stream);
+int cvd_gather_pad_bwd(const float* dpad, int p_ctotal, int p_coff, const float* src, int s_ctotal, int s_coff, int s_pad,
+                       float* dsrc, int ds_ctotal, int ds_coff, int ds_pad, int N, int hs, int ws, int C, int upsample,
+                       int mode, int accumulate, void* stream);
+
+/* out[c] += sum over pixels of x[p, c_off + c] (bias gradient of a conv without BatchNorm); C a power of two <= 256. */
+int cvd_channel_sum(const float* x, int c_total, int c_off, int C, long long npix, float* out, void* stream);
 
 #ifdef __cplusplus
 }
