@@ -152,6 +152,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer pass")
+    ap.add_argument("--workload", default="mc", choices=["mc", "monodepth2"],
+                    help="mc = BASELINE.json configs[1] (the headline); monodepth2 = configs C4's model at 192x640 BS4 per GPU "
+                         "(secondary line: no roofline / CPU legs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -179,7 +182,20 @@ def main():
     sd = default_init_state(0)
     sd["pred_layer.weight"] = sd["pred_layer.weight"] * 0.1
     sd["pred_layer.bias"] = torch.full((1,), math.log(2.0))
-    model = MannequinChallengeModel(state_dict=sd, precision=args.precision)
+    H, W, metric = globals()["H"], globals()["W"], METRIC
+    workload = ("mannequin_challenge hourglass fine-tune step, 224x384, 4 frame pairs (8 frames) per GPU, "
+                "hierarchical2 pairs of 50 synthetic frames, Adam lr 4e-4")
+    weights = "seeded default-scale init, output head centred on the scene depth (mc.pth unreachable: no network)"
+    if args.workload == "monodepth2":
+        from consistent_depth_b200.monodepth.monodepth2_model import Monodepth2Model
+        H, W, metric = 192, 640, "frame-pairs/sec fine-tune (monodepth2 192x640 BS4)"
+        model = Monodepth2Model(precision=args.precision)
+        workload = ("monodepth2 (ResNet-18 encoder + depth decoder, 320x1024 feed) fine-tune step, 192x640, 4 frame pairs "
+                    "(8 frames) per GPU, hierarchical2 pairs of 50 synthetic frames, Adam lr 4e-5")
+        weights = "seeded default-scale init (stock checkpoint unreachable: no network)"
+        args.no_roofline = args.no_cpu_baseline = True
+    else:
+        model = MannequinChallengeModel(state_dict=sd, precision=args.precision)
     video = SyntheticVideo(NFRAMES, H, W, dev, seed=1234 + 2)          # config #2
     n_pairs = len(video.pairs)
     gperm = torch.Generator().manual_seed(0)
@@ -268,15 +284,14 @@ def main():
                     "sample": "3 steps x 1 frame pair (2 frames 224x384) after 1 warm-up: fwd+loss+bwd+Adam, CPU PyTorch fp32 oracle"}
     if rank == 0:
         print(json.dumps({
-            "metric": METRIC, "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric, "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3-split tensor-core MMA, fp32 accumulate/storage" if args.precision == 3 else "bf16 MMA, fp32 accumulate/storage",
             "data": "synthetic",
-            "config": {"workload": "mannequin_challenge hourglass fine-tune step, 224x384, 4 frame pairs (8 frames) per GPU, "
-                                   "hierarchical2 pairs of 50 synthetic frames, Adam lr 4e-4",
+            "config": {"workload": workload,
                        "global_batch": BS * world, "parallelism": f"dp{world}",
-                       "l2_policy": "per-step working set (~6 GB of activations) >> 126 MB L2; no explicit flush",
-                       "weights": "seeded default-scale init, output head centred on the scene depth (mc.pth unreachable: no network)"},
+                       "l2_policy": "per-step working set (several GB of activations) >> 126 MB L2; no explicit flush",
+                       "weights": weights},
             "roofline": roofline, "roofline_loss_kernel": roof_loss, "cpu_baseline": cpu_base, "e2e": e2e,
             "gpu_launches": gpu_launches, "clocks": clocks, "final_loss": loss_last, "peaks_source": pk_src,
         }), flush=True)
