@@ -13,6 +13,9 @@ fixtures hold only what the real reference modules produced for them:
   monodepth2_small.npz: monodepth/monodepth2/networks ResnetEncoder(18) + DepthDecoder driven exactly as
                       monodepth/monodepth2_model.py:63-89 does (bicubic in, disp0, bicubic out, reciprocal),
                       train mode, + grads of the consistency loss (lambda_view_baseline = 1), BN running stats
+  midas_small.npz   : monodepth/midas_v2/midas_net.py MidasNet (trunk = torchvision resnext101_32x8d in place of the
+                      unreachable torch.hub WSL model, same layer graph) driven as monodepth/midas_v2_model.py:52-69
+                      does, train mode, + grads of the consistency loss (lambda_view_baseline = 1e-4), BN running stats
   finetune_steps.npz: depth_fine_tuning.py:261-283 inner loop (model -> zero_grad -> JointLoss ->
                       backward -> step), 3 steps on one pair
 """
@@ -26,7 +29,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
-from oracle import ref_import, synth, hourglass_oracle as ho, monodepth2_oracle as m2  # noqa: E402
+from oracle import ref_import, synth, hourglass_oracle as ho, monodepth2_oracle as m2, midas_oracle as mo  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
@@ -167,6 +170,56 @@ def gen_monodepth2():
     print("monodepth2 loss", out["loss"], "ngrads", len(names), "depth range", float(depth.min()), float(depth.max()))
 
 
+MIDAS_CASE = dict(seed=61, H=96, W=160, pairs=[(0, 1)])
+MIDAS_FULL_GRADS = ("pretrained.layer1.0.weight", "pretrained.layer1.1.weight", "pretrained.layer1.4.0.conv2.weight",
+                    "pretrained.layer2.0.downsample.1.weight", "pretrained.layer3.11.bn2.bias", "pretrained.layer4.2.bn3.weight",
+                    "scratch.refinenet1.resConfUnit1.conv1.bias", "scratch.refinenet4.resConfUnit2.conv2.bias",
+                    "scratch.output_conv.2.weight", "scratch.output_conv.4.weight", "scratch.output_conv.4.bias")
+MIDAS_BUFS = ("pretrained.layer1.1.running_mean", "pretrained.layer1.1.running_var", "pretrained.layer2.0.downsample.1.running_var",
+              "pretrained.layer3.22.bn3.running_mean", "pretrained.layer4.2.bn2.running_var")
+
+
+def gen_midas():
+    import warnings
+    import torchvision
+    warnings.filterwarnings("ignore")
+    # blocks.py:27-29 pulls the trunk from torch.hub (no network here): torchvision defines the identical layer graph
+    torch.hub.load = lambda *a, **k: torchvision.models.resnext101_32x8d(weights=None)
+    from monodepth.midas_v2.midas_net import MidasNet
+    c = MIDAS_CASE
+    seed, H, W = c["seed"], c["H"], c["W"]
+    sd = mo.midas_init_state(seed)
+    net = MidasNet(non_negative=True)
+    net.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
+    net.train()
+    batch = synth.make_pair_batch(seed, c["pairs"], H, W)
+    images = torch.tensor(batch["images"])
+    # the adapter body, midas_v2_model.py:52-69 (the class itself downloads a checkpoint)
+    x = images.reshape(-1, 3, H, W)
+    mean = torch.Tensor([0.485, 0.456, 0.406]).reshape(1, -1, 1, 1)
+    std = torch.Tensor([0.229, 0.224, 0.225]).reshape(1, -1, 1, 1)
+    output = net((x - mean) / std)
+    depth = output.reshape(1, 2, H, W).reciprocal()
+    crit = ref_joint_loss(1.0, 1e-4, torch.float32)
+    loss, meta = crit(depth, to_metadata(batch, torch.float32))
+    loss.backward()
+    out = {"disparity": output.detach().numpy(), "depth": depth.detach().numpy(), "loss": loss.detach().numpy()}
+    params = dict(net.named_parameters())
+    names, norms = [], []
+    for k, p in params.items():
+        if p.grad is None:
+            continue
+        names.append(k); norms.append(float(p.grad.double().norm()))
+    out["grad_names"] = np.array(names); out["grad_norms"] = np.array(norms)
+    for k in MIDAS_FULL_GRADS:
+        out["grad::" + k] = params[k].grad.numpy()
+    st = net.state_dict()
+    for k in MIDAS_BUFS:
+        out["buf::" + k] = st[k].numpy()
+    np.savez_compressed(os.path.join(OUT, "midas_small.npz"), **out)
+    print("midas loss", out["loss"], "ngrads", len(names), "disparity range", float(output.min()), float(output.max()))
+
+
 def gen_adam():
     import optimizer
     p0 = synth.normal(31, 1, (1003,), 0.1)
@@ -214,14 +267,14 @@ def gen_finetune():
 
 def main():
     ap = argparse.ArgumentParser(description=__doc__)
-    ap.add_argument("--only", default=None, help="generate one fixture family: consistency|adam|hourglass|finetune|monodepth2")
+    ap.add_argument("--only", default=None, help="generate one fixture family: consistency|adam|hourglass|finetune|monodepth2|midas")
     only = ap.parse_args().only
     ref_import.setup()
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     os.makedirs(OUT, exist_ok=True)
     gens = {"consistency": gen_consistency, "adam": gen_adam, "hourglass": gen_hourglass, "finetune": gen_finetune,
-            "monodepth2": gen_monodepth2}
+            "monodepth2": gen_monodepth2, "midas": gen_midas}
     for name, fn in gens.items():
         if only is None or only == name:
             fn()
