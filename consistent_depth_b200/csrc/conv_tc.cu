@@ -373,11 +373,18 @@ __device__ __forceinline__ void pack_one(const float* __restrict__ w, int cin_w,
     const int tap = (int)(i / ((long long)cin_pad * cout_pad));
     const int ky = tap / k, kx = tap - ky * k;
     float v = 0.f;
-    if (!transpose_flip) {
-      if (c < cin_w && nn < cout_w) v = w[(((size_t)nn * cin_w + c) * k + ky) * k + kx];
-    } else {
-      // GEMM "cin" = forward Cout (w dim 0), GEMM "cout" = forward Cin (w dim 1)
-      if (c < cout_w && nn < cin_w) v = w[(((size_t)c * cin_w + nn) * k + (k - 1 - ky)) * k + (k - 1 - kx)];
+    const int flip = transpose_flip & 1, gs = transpose_flip >> 8;   // gs > 0: grouped conv, `gs` channels per group
+    if (gs == 0) {
+      if (!flip) {
+        if (c < cin_w && nn < cout_w) v = w[(((size_t)nn * cin_w + c) * k + ky) * k + kx];
+      } else {
+        // GEMM "cin" = forward Cout (w dim 0), GEMM "cout" = forward Cin (w dim 1)
+        if (c < cout_w && nn < cin_w) v = w[(((size_t)c * cin_w + nn) * k + (k - 1 - ky)) * k + (k - 1 - kx)];
+      }
+    } else if (c < cin_w && nn < cout_w && c / gs == nn / gs) {
+      // grouped weights (Cout, gs, k, k) expanded block-diagonally into a dense cin_w x cout_w chunk (cin_w == cout_w)
+      if (!flip) v = w[(((size_t)nn * gs + c % gs) * k + ky) * k + kx];
+      else       v = w[(((size_t)c * gs + nn % gs) * k + (k - 1 - ky)) * k + (k - 1 - kx)];
     }
     const int nj = nn >> 8, nl = nn & 255;
     const int cp = min(256, cout_pad - (nj << 8));                 // columns of this chunk
@@ -409,7 +416,7 @@ struct PackDesc { const float* w; uint8_t* out; int cin, cout, k, flip; };
 __global__ void pack_weights_batch_kernel(const PackDesc* __restrict__ descs, int nsplit)
 {
   const PackDesc d = descs[blockIdx.y];
-  const int kc = d.flip ? d.cout : d.cin, nc = d.flip ? d.cin : d.cout;
+  const int kc = (d.flip & 1) ? d.cout : d.cin, nc = (d.flip & 1) ? d.cin : d.cout;
   pack_one(d.w, d.cin, d.cout, d.k, d.flip, (kc + 15) / 16 * 16, (nc + 15) / 16 * 16, nsplit, d.out,
            (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
 }
@@ -430,7 +437,8 @@ extern "C" int cvd_conv_pack_weights(const float* w_oihw, int cin, int cout, int
   CVD_CHECK_ARG(w_oihw && packed, "cvd_conv_pack_weights: null pointer");
   CVD_CHECK_ARG(precision == 1 || precision == 3, "cvd_conv_pack_weights: precision must be 1 or 3");
   // forward: GEMM K-channels = cin, N = cout; dgrad: K-channels = cout, N = cin
-  const int kc = transpose_flip ? cout : cin, nc = transpose_flip ? cin : cout;
+  CVD_CHECK_ARG((transpose_flip >> 8) == 0 || cin == cout, "cvd_conv_pack_weights: grouped chunks must be square");
+  const int kc = (transpose_flip & 1) ? cout : cin, nc = (transpose_flip & 1) ? cin : cout;
   const int cin_pad = round_up(kc, 16), cout_pad = round_up(nc, 16);
   const long long total = (long long)cin_pad * cout_pad * k * k;
   long long blocks = (total + 255) / 256; if (blocks > 4096) blocks = 4096;

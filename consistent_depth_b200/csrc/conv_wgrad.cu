@@ -33,6 +33,7 @@ struct WgArgs {
   float* dw;
   int N, H, W, cin, cout, cin_w, cout_w, k, pad;   // cin/cout padded to 16; *_w = real (dW extents)
   int dw_ci_stride;                                // Cin of the whole dW tensor (>= cin_w when this launch is a chunk)
+  int group;                                       // > 0: grouped conv chunk, dW is (Cout, group, k, k): only same-group entries are kept
   int nsplit;
   int x_is_m;                   // 1: M = X channels (Cin), N = G channels (Cout)
   int Mrows, mblk;              // MMA M (64/128), number of M blocks
@@ -171,7 +172,10 @@ wgrad_tc_kernel(const WgArgs p)
             for (int i = 0; i < 16; ++i) {
               const int nn = c16 + i;
               const int ci = p.x_is_m ? m : nn, co = p.x_is_m ? nn : m;
-              if (ci < p.cin_w && co < p.cout_w) atomicAdd(p.dw + ((size_t)co * p.dw_ci_stride + ci) * kk + tap, v[i]);
+              if (ci < p.cin_w && co < p.cout_w) {
+                if (p.group == 0) atomicAdd(p.dw + ((size_t)co * p.dw_ci_stride + ci) * kk + tap, v[i]);
+                else if (ci / p.group == co / p.group) atomicAdd(p.dw + ((size_t)co * p.group + ci % p.group) * kk + tap, v[i]);
+              }
             }
           }
         }
@@ -207,7 +211,15 @@ static void sub_view(int& c_off, int& n0, int& gap, int s)
 }
 
 static int wgrad_impl(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oihw,
-                      int N, int H, int W, int cin, int cout, int k, int precision, int dw_ci_stride, void* stream);
+                      int N, int H, int W, int cin, int cout, int k, int precision, int dw_ci_stride, void* stream, int group = 0);
+
+extern "C" int cvd_conv_wgrad_grouped(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_ogkk,
+                                      int N, int H, int W, int c, int group_size, int k, int precision, void* stream)
+{
+  CVD_CHECK_ARG(gsrc && xsrc && dw_ogkk && gsrc->x && xsrc->x, "cvd_conv_wgrad_grouped: null pointer");
+  CVD_CHECK_ARG(c > 0 && c <= 256 && group_size > 0 && c % group_size == 0, "cvd_conv_wgrad_grouped: c=%d group_size=%d", c, group_size);
+  return wgrad_impl(gsrc, xsrc, dw_ogkk, N, H, W, c, c, k, precision, -1, stream, group_size);
+}
 
 extern "C" int cvd_conv_wgrad(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oihw,
                               int N, int H, int W, int cin, int cout, int k, int precision, void* stream)
@@ -231,7 +243,7 @@ extern "C" int cvd_conv_wgrad(const cvd_src_t* gsrc, const cvd_src_t* xsrc, floa
 }
 
 static int wgrad_impl(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oihw,
-                      int N, int H, int W, int cin, int cout, int k, int precision, int dw_ci_stride, void* stream)
+                      int N, int H, int W, int cin, int cout, int k, int precision, int dw_ci_stride, void* stream, int group)
 {
   CVD_CHECK_ARG(precision == 1 || precision == 3, "cvd_conv_wgrad: precision must be 1 or 3");
   CVD_CHECK_ARG(k >= 1 && k <= 11 && (k & 1), "cvd_conv_wgrad: k=%d unsupported", k);
@@ -249,7 +261,7 @@ static int wgrad_impl(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oi
   p.g = make_view(gsrc, round_up(cout, 4)); p.x = make_view(xsrc, round_up(cin, 4));
   p.dw = dw_oihw; p.N = N; p.H = H; p.W = W; p.k = k; p.pad = (k - 1) / 2;
   p.cin_w = cin; p.cout_w = cout; p.cin = round_up(cin, 16); p.cout = round_up(cout, 16);
-  p.dw_ci_stride = dw_ci_stride;
+  p.dw_ci_stride = dw_ci_stride; p.group = group;
   p.nsplit = precision;
   CVD_CHECK_ARG(p.cin <= 256 && p.cout <= 256, "cvd_conv_wgrad: channel counts above 256 unsupported");
   p.x_is_m = p.cin >= p.cout;

@@ -34,15 +34,17 @@ def _numel(s):
 class Mono2Params:
     """Flat parameter / gradient / BN-buffer storage of a Monodepth2Model (same interface as McParams)."""
 
-    def __init__(self, device):
+    def __init__(self, device, shapes=None, is_buffer=None, counter_key="encoder.bn1.num_batches_tracked"):
         self.dev = torch.device(device)
-        self.sd_shapes = arch.state_dict_shapes()
+        self.sd_shapes = shapes if shapes is not None else arch.state_dict_shapes()
+        is_buffer = is_buffer or arch.is_buffer
+        self.counter_key = counter_key
         self.pmap, off = {}, 0
         self.bmap, boff = {}, 0
         for k, s in self.sd_shapes.items():
             if k.endswith("num_batches_tracked"):
                 continue
-            if arch.is_buffer(k):
+            if is_buffer(k):
                 self.bmap[k] = (boff, s)
                 boff += _numel(s)
             else:
@@ -80,8 +82,8 @@ class Mono2Params:
             self._p(k).copy_(torch.as_tensor(sd[k], dtype=torch.float32).reshape(self.pmap[k][1]))
         for k, (o, s) in self.bmap.items():
             self.buf_flat[o:o + s[0]].copy_(torch.as_tensor(sd[k], dtype=torch.float32))
-        if "encoder.bn1.num_batches_tracked" in sd:
-            self.num_batches_tracked = int(sd["encoder.bn1.num_batches_tracked"])
+        if self.counter_key in sd:
+            self.num_batches_tracked = int(sd[self.counter_key])
         if "height" in sd and "width" in sd:
             self.feed_size = (int(sd["height"]), int(sd["width"]))
 

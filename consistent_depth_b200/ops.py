@@ -165,8 +165,12 @@ def make_pack_table(entries, device):
     import numpy as np
     dt = np.dtype([("w", "<u8"), ("out", "<u8"), ("cin", "<i4"), ("cout", "<i4"), ("k", "<i4"), ("flip", "<i4")])
     arr = np.zeros(len(entries), dtype=dt)
-    for i, (w, out, flip) in enumerate(entries):
-        arr[i] = (w.data_ptr(), out.data_ptr(), w.shape[1], w.shape[0], w.shape[2], 1 if flip else 0)
+    for i, e in enumerate(entries):
+        w, out, flip = e[0], e[1], e[2]
+        if len(e) == 3:
+            arr[i] = (w.data_ptr(), out.data_ptr(), w.shape[1], w.shape[0], w.shape[2], 1 if flip else 0)
+        else:       # (w rows of a grouped weight, packed, flip, chunk width, group size): block-diagonal chunk
+            arr[i] = (w.data_ptr(), out.data_ptr(), e[3], e[3], w.shape[2], (1 if flip else 0) | (e[4] << 8))
     t = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
     t._keep = [e[0] for e in entries] + [e[1] for e in entries]
     return t, len(entries)
@@ -275,3 +279,52 @@ def gather_pad_bwd(dpad, p_coff, src, s_coff, s_pad, dsrc, ds_coff, ds_pad, Cn, 
 def channel_sum(x, c_off, Cn, out):
     _lib.check(_lib.lib().cvd_channel_sum(_lib.ptr(x), x.shape[-1], c_off, Cn, C.c_longlong(x.numel() // x.shape[-1]),
                                           _lib.ptr(out), _lib.stream()), "cvd_channel_sum")
+
+
+# ---------------------------------------------------------------- MiDaS-v2 passes
+def conv_wgrad_grouped(gsrc, xsrc, dw_rows, N, H, W, c, group_size, k, precision=3):
+    _lib.check(_lib.lib().cvd_conv_wgrad_grouped(C.byref(gsrc), C.byref(xsrc), _lib.ptr(dw_rows), N, H, W, c, group_size, k,
+                                                 precision, _lib.stream()), "cvd_conv_wgrad_grouped")
+
+
+def pack_weights_grouped(w_rows, c, group_size, transpose_flip=False, precision=3):
+    """Rows [chunk, chunk+c) of a (Cout, group_size, k, k) grouped weight -> packed dense c x c block-diagonal chunk."""
+    k = w_rows.shape[2]
+    out = torch.empty(packed_bytes(c, c, k, precision), dtype=torch.uint8, device=w_rows.device)
+    _lib.check(_lib.lib().cvd_conv_pack_weights(_lib.ptr(w_rows), c, c, k, (1 if transpose_flip else 0) | (group_size << 8),
+                                                precision, _lib.ptr(out), _lib.stream()), "cvd_conv_pack_weights")
+    return out
+
+
+def image_normalize(img, out4, mean, std):
+    N, _, H, W = img.shape
+    m, s = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    _lib.check(_lib.lib().cvd_image_normalize_nhwc4(_lib.ptr(img), N, H, W, m, s, _lib.ptr(out4), _lib.stream()),
+               "cvd_image_normalize_nhwc4")
+
+
+def relu_add(x, other, out):
+    _lib.check(_lib.lib().cvd_relu_add(_lib.ptr(x), _lib.ptr(other), _lib.ptr(out), C.c_longlong(x.numel()), _lib.stream()),
+               "cvd_relu_add")
+
+
+def up2_bilinear(x, r, relu_r, out, align_corners):
+    N, h, w, Cn = x.shape
+    _lib.check(_lib.lib().cvd_up2_bilinear_fwd(_lib.ptr(x), _lib.ptr(r), 1 if relu_r else 0, N, h, w, Cn,
+                                               1 if align_corners else 0, _lib.ptr(out), _lib.stream()), "cvd_up2_bilinear_fwd")
+
+
+def up2_bilinear_bwd(dout, dx, align_corners, accumulate):
+    N, h, w, Cn = dx.shape
+    _lib.check(_lib.lib().cvd_up2_bilinear_bwd(_lib.ptr(dout), N, h, w, Cn, 1 if align_corners else 0, _lib.ptr(dx),
+                                               1 if accumulate else 0, _lib.stream()), "cvd_up2_bilinear_bwd")
+
+
+def recip_relu(raw4, depth):
+    _lib.check(_lib.lib().cvd_recip_relu_fwd(_lib.ptr(raw4), _lib.ptr(depth), C.c_longlong(depth.numel()), _lib.stream()),
+               "cvd_recip_relu_fwd")
+
+
+def recip_relu_bwd(ddepth, depth, raw4, draw4):
+    _lib.check(_lib.lib().cvd_recip_relu_bwd(_lib.ptr(ddepth), _lib.ptr(depth), _lib.ptr(raw4), _lib.ptr(draw4),
+                                             C.c_longlong(depth.numel()), _lib.stream()), "cvd_recip_relu_bwd")

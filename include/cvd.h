@@ -135,7 +135,11 @@ typedef struct {
  * hi(/lo) UMMA core-matrix blobs, one per (tap, 16-channel k-block), that the
  * conv kernel streams with cp.async.bulk.  transpose_flip != 0 builds the dgrad
  * operand (Cin<->Cout swapped, taps rotated 180 degrees).
- * precision: 1 = bf16, 3 = bf16x3 split (hi+lo, fp32-class). */
+ * precision: 1 = bf16, 3 = bf16x3 split (hi+lo, fp32-class).
+ * Grouped convolutions (ResNeXt's 3x3, groups=32): pass group_size << 8 in the upper bits of transpose_flip and
+ * cin == cout == the chunk width (a multiple of group_size); w then points at rows [chunk .. chunk+cout) of the
+ * (Cout, group_size, k, k) weight and is expanded block-diagonally, so the dense kernel computes the grouped conv
+ * of that channel chunk. */
 size_t cvd_conv_packed_bytes(int cin, int cout, int k, int precision);
 int cvd_conv_pack_weights(const float* w_oihw, int cin, int cout, int k, int transpose_flip,
                           int precision, void* packed, void* stream);
@@ -170,6 +174,11 @@ typedef struct {
 int cvd_conv_fwd_bn(const cvd_src_t* src, const void* packed_w, const float* bias,
                     const cvd_dst_t* dst, int N, int H, int W, int cin, int cout, int k,
                     int precision, int flags, const cvd_bn_t* bn, void* stream);
+
+/* Weight gradient of one channel chunk of a grouped convolution (see cvd_conv_pack_weights): gsrc / xsrc are views
+ * of the chunk's c output / input channels, dw points at the chunk's rows of the (Cout, group_size, k, k) gradient. */
+int cvd_conv_wgrad_grouped(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_ogkk,
+                           int N, int H, int W, int c, int group_size, int k, int precision, void* stream);
 
 /* Weight gradient of the same convolution: dW (fp32 OIHW, [cout][cin][k][k]) += sum over all
  * pixels of G (x) X, the wgrad half of autograd's conv backward (depth_fine_tuning.py:282).
@@ -293,6 +302,30 @@ int cvd_gather_pad_bwd(const float* dpad, int p_ctotal, int p_coff, const float*
 
 /* out[c] += sum over pixels of x[p, c_off + c] (bias gradient of a conv without BatchNorm); C a power of two <= 256. */
 int cvd_channel_sum(const float* x, int c_total, int c_off, int C, long long npix, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * MiDaS-v2 network: the passes around the conv engine.  NHWC fp32, C multiples of 4.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* (images - mean) / std per channel (midas_v2_model.py:58-59): (N,3,H,W) -> (N,H,W,4), 4th channel 0.
+ * mean3_host / std3_host: 3 host floats each (passed by value to the kernel). */
+int cvd_image_normalize_nhwc4(const float* img_nchw, int N, int H, int W, const float* mean3_host,
+                              const float* std3_host, float* out_nhwc4, void* stream);
+
+/* out = relu(x) + other (other may be NULL): the skip term of ResidualConvUnit (blocks.py:111-117, whose in-place
+ * ReLU makes the skip relu(x)) and the FeatureFusionBlock sum (blocks.py:146-147); the conv then accumulates into out. */
+int cvd_relu_add(const float* x, const float* other, float* out, long long n, void* stream);
+
+/* out (N,2h,2w,C) = bilinear_x2(x (N,h,w,C)) [+ r or relu(r)], align_corners as given (blocks.py:151-153 True,
+ * midas_net.py:40 False).  Backward (gather form): dx (N,h,w,C) (+)= transpose applied to dout. */
+int cvd_up2_bilinear_fwd(const float* x, const float* r, int relu_r, int N, int h, int w, int C, int align_corners,
+                         float* out, void* stream);
+int cvd_up2_bilinear_bwd(const float* dout, int N, int h, int w, int C, int align_corners, float* dx, int accumulate, void* stream);
+
+/* depth = 1 / relu(raw) (midas_net.py:43 ReLU + midas_v2_model.py:67 reciprocal) on channel 0 of 4-channel pixels;
+ * backward: draw4 = (raw > 0 ? -ddepth * depth^2 : 0, 0, 0, 0). */
+int cvd_recip_relu_fwd(const float* raw4, float* depth, long long n, void* stream);
+int cvd_recip_relu_bwd(const float* ddepth, const float* depth, const float* raw4, float* draw4, long long n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -62,5 +62,6 @@ def test_registry_surface():
     assert (MannequinChallengeModel.align, MannequinChallengeModel.learning_rate, MannequinChallengeModel.lambda_view_baseline) == (16, 0.0004, 0.1)
     with pytest.raises(ValueError):
         get_depth_model("nope")
-    with pytest.raises(NotImplementedError):
-        get_depth_model("midas2")
+    from consistent_depth_b200.monodepth.midas_v2_model import MidasV2Model
+    assert get_depth_model("midas2") is MidasV2Model
+    assert (MidasV2Model.align, MidasV2Model.learning_rate, MidasV2Model.lambda_view_baseline) == (32, 0.0001, 0.0001)

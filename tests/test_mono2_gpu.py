@@ -313,6 +313,26 @@ def test_mono2_forward_matches_oracle_and_reference_golden():
     assert int(st["encoder.bn1.num_batches_tracked"]) == 1 and (st["height"], st["width"]) == tuple(c["feed"])
 
 
+def test_mono2_eval_mode_forward_is_tight():
+    """model.eval() (running statistics): the composition of every forward kernel without batch-statistics amplification."""
+    from consistent_depth_b200.monodepth.monodepth2_model import Monodepth2Model
+    c, batch, sd = _case()
+    sd = dict(sd)
+    for i, k in enumerate(sd):
+        if k.endswith("running_mean"):
+            sd[k] = synth.uniform(7, 3000 + i, sd[k].shape, -0.2, 0.2)
+        elif k.endswith("running_var"):
+            sd[k] = synth.uniform(7, 6000 + i, sd[k].shape, 0.5, 1.5)
+    model = Monodepth2Model(state_dict=sd, feed_size=c["feed"])
+    model.eval()
+    with torch.no_grad():
+        depth = model(torch.tensor(batch["images"], device=DEV))
+    P, buffers = m2.to_torch(sd, dtype=torch.float64)
+    with torch.no_grad():
+        want = m2.estimate_depth(torch.tensor(batch["images"], dtype=torch.float64), P, buffers, c["feed"], train=False)
+    np.testing.assert_allclose(depth.cpu().numpy(), want.numpy(), rtol=1e-4)
+
+
 def test_mono2_backward_matches_oracle():
     from consistent_depth_b200.monodepth.monodepth2_model import Monodepth2Model
     from consistent_depth_b200.monodepth import mono2_arch
