@@ -152,7 +152,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer pass")
-    ap.add_argument("--workload", default="mc", choices=["mc", "monodepth2"],
+    ap.add_argument("--workload", default="mc", choices=["mc", "monodepth2", "midas2"],
                     help="mc = BASELINE.json configs[1] (the headline); monodepth2 = configs C4's model at 192x640 BS4 per GPU "
                          "(secondary line: no roofline / CPU legs)")
     args = ap.parse_args()
@@ -193,6 +193,15 @@ def main():
         workload = ("monodepth2 (ResNet-18 encoder + depth decoder, 320x1024 feed) fine-tune step, 192x640, 4 frame pairs "
                     "(8 frames) per GPU, hierarchical2 pairs of 50 synthetic frames, Adam lr 4e-5")
         weights = "seeded default-scale init (stock checkpoint unreachable: no network)"
+        args.no_roofline = args.no_cpu_baseline = True
+    elif args.workload == "midas2":
+        from consistent_depth_b200.monodepth.midas_v2_model import MidasV2Model
+        H, W, metric = 384, 672, "frame-pairs/sec fine-tune (midas2 384x672 BS1 per GPU)"
+        globals()["BS"] = 1                      # C3: global batch 8 on 8 GPUs = 1 pair per GPU
+        model = MidasV2Model(pretrained=False, precision=args.precision)
+        workload = ("MiDaS v2 (ResNeXt-101 32x8d + refinement decoder) fine-tune step, 384x672, 1 frame pair (2 frames) per GPU, "
+                    "hierarchical2 pairs of 50 synthetic frames, Adam lr 1e-4")
+        weights = "seeded default-scale init, positive output layer (model-f46da743.pt unreachable: no network)"
         args.no_roofline = args.no_cpu_baseline = True
     else:
         model = MannequinChallengeModel(state_dict=sd, precision=args.precision)
