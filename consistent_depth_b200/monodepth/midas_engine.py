@@ -24,6 +24,7 @@ from . import midas_arch as arch
 from .mono2_engine import Mono2Engine, Mono2Params, _Act, _BN, _plain
 
 CHUNK = 64          # channel width of one block-diagonal launch of a grouped conv
+BRANCHES = 4        # the chunk launches of one grouped conv are independent: forked onto this many graph branches
 
 
 class MidasParams(Mono2Params):
@@ -62,6 +63,8 @@ class MidasEngine(Mono2Engine):
         gs = width // arch.GROUPS
         Wt = self._p(wkey)
         N, prec = self.N, self.prec
+        branches = [[] for _ in range(BRANCHES)]
+        scratches = [bn2.scratch] + [ops.bn_scratch(self.dev) for _ in range(BRANCHES - 1)] if bn2 is not None else None
         for j in range(width // CHUNK):
             c0 = j * CHUNK
             pk = self._packed(CHUNK, CHUNK, 3)
@@ -69,11 +72,12 @@ class MidasEngine(Mono2Engine):
             s = ops.make_src(ops.View(y1, c0), bn1.a, bn1.b, True)
             d = ops.make_dst(ops.View(dst, c0))
             fused = None
-            if bn2 is not None:
-                fused = ops.make_bn(bn2.scratch, bn2.a, bn2.b, bn2.rstd, bn2.mean, bn2.gamma[c0:c0 + CHUNK], bn2.beta[c0:c0 + CHUNK],
-                                    bn2.rm[c0:c0 + CHUNK], bn2.rv[c0:c0 + CHUNK])
-            self.fwd.append(lambda s=s, pk=pk, d=d, fused=fused: ops.conv(
+            if bn2 is not None:      # concurrent launches: one statistics scratch per branch
+                fused = ops.make_bn(scratches[j % BRANCHES], bn2.a, bn2.b, bn2.rstd, bn2.mean, bn2.gamma[c0:c0 + CHUNK],
+                                    bn2.beta[c0:c0 + CHUNK], bn2.rm[c0:c0 + CHUNK], bn2.rv[c0:c0 + CHUNK])
+            branches[j % BRANCHES].append(lambda s=s, pk=pk, d=d, fused=fused: ops.conv(
                 s, pk, None, d, N, h, w, CHUNK, CHUNK, 3, prec, 0, bn=fused if self.train_mode else None))
+        self.fwd.append(("par", branches))
         if bn2 is not None:
             self._bn_eval(bn2)
 
@@ -82,16 +86,18 @@ class MidasEngine(Mono2Engine):
         gs = width // arch.GROUPS
         Wt, dW = self._p(wkey), self._g(wkey)
         N, prec = self.N, self.prec
+        branches = [[] for _ in range(BRANCHES)]
         for j in range(width // CHUNK):
             c0 = j * CHUNK
             g = g_of_chunk(c0)
             x = ops.make_src(ops.View(y1, c0), bn1.a, bn1.b, True)
             dw = dW[c0:c0 + CHUNK]
-            self.bwd.append(lambda g=g, x=x, dw=dw: ops.conv_wgrad_grouped(g, x, dw, N, h, w, CHUNK, gs, 3, prec))
+            branches[j % BRANCHES].append(lambda g=g, x=x, dw=dw: ops.conv_wgrad_grouped(g, x, dw, N, h, w, CHUNK, gs, 3, prec))
             pk = self._packed(CHUNK, CHUNK, 3)
             self.pack_bwd.append((Wt[c0:c0 + CHUNK], pk, True, CHUNK, gs))
             d = ops.make_dst(ops.View(d1, c0))
-            self.bwd.append(lambda g=g, pk=pk, d=d: ops.conv(g, pk, None, d, N, h, w, CHUNK, CHUNK, 3, prec, 0))
+            branches[(j + BRANCHES // 2) % BRANCHES].append(lambda g=g, pk=pk, d=d: ops.conv(g, pk, None, d, N, h, w, CHUNK, CHUNK, 3, prec, 0))
+        self.bwd.append(("par", branches))
 
     # ------------------------------------------------------------------ plan
     def _build(self):
@@ -338,8 +344,7 @@ class MidasEngine(Mono2Engine):
         assert images.shape == (self.N, 3, self.H, self.W), images.shape
         ops.image_normalize(images.contiguous(), self.img4, arch.NORM_MEAN, arch.NORM_STD)
         ops.pack_batch(self.pack_fwd_tab[0], self.pack_fwd_tab[1], self.prec)
-        for f in self.fwd:
-            f()
+        self._run(self.fwd)
         if self.train_mode:
             self.P.num_batches_tracked += 1
         return self.depth

@@ -392,13 +392,43 @@ class Mono2Engine:
         return dict(t=R1, pad=1, mode=ops.GATHER_ELU, C=Cd, h=2 * h, w=2 * w, act=None, dR=dR1)
 
     # ------------------------------------------------------------------ execution
+    def _run(self, plan):
+        """Plan entries are callables (serial) or ("par", [branch, ...]): independent branches forked onto side streams and
+        joined back (parallel branches of the captured CUDA graph), as in McEngine._run."""
+        import os
+        multi = os.environ.get("CVD_MULTI_STREAM", "1") == "1"
+        main = torch.cuda.current_stream() if multi else None
+        if not hasattr(self, "side_streams"):
+            self.side_streams = []
+        for op in plan:
+            if not isinstance(op, tuple):
+                op()
+                continue
+            branches = [b for b in op[1] if b]
+            if not multi or len(branches) <= 1:
+                for br in branches:
+                    for f in br:
+                        f()
+                continue
+            while len(self.side_streams) < len(branches) - 1:
+                self.side_streams.append(torch.cuda.Stream(device=self.dev))
+            for i, br in enumerate(branches[1:]):
+                s = self.side_streams[i]
+                s.wait_stream(main)
+                with torch.cuda.stream(s):
+                    for f in br:
+                        f()
+            for f in branches[0]:
+                f()
+            for i in range(len(branches) - 1):
+                main.wait_stream(self.side_streams[i])
+
     def forward(self, images):
         """images (N,3,H,W) BGR in [0,1] (CUDA) -> depth (N,H,W) (engine-owned buffer)."""
         assert images.shape == (self.N, 3, self.H, self.W), images.shape
         ops.bicubic_image(images.contiguous(), self.img4)
         ops.pack_batch(self.pack_fwd_tab[0], self.pack_fwd_tab[1], self.prec)
-        for f in self.fwd:
-            f()
+        self._run(self.fwd)
         if self.train_mode:
             self.P.num_batches_tracked += 1
         return self.depth
@@ -407,5 +437,4 @@ class Mono2Engine:
         """grad_depth (N,H,W) = d loss / d depth; accumulates into the flat gradient buffer (zero it first)."""
         self.grad_depth = grad_depth.contiguous()
         ops.pack_batch(self.pack_bwd_tab[0], self.pack_bwd_tab[1], self.prec)
-        for f in self.bwd:
-            f()
+        self._run(self.bwd)
