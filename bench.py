@@ -315,13 +315,15 @@ def measure_rooflines(model, step, batch, load, pk, pk_src):
     recs = []
     orig_conv = ops.conv
 
-    def timed_conv(src, packed, bias, dst, N, h, w, cin, cout, k, precision=3, flags=0):
+    def timed_conv(src, packed, bias, dst, N, h, w, cin, cout, k, precision=3, flags=0, bn=None):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        orig_conv(src, packed, bias, dst, N, h, w, cin, cout, k, precision, flags)
+        orig_conv(src, packed, bias, dst, N, h, w, cin, cout, k, precision, flags, bn=bn)
         b.record()
         recs.append((a, b, 2.0 * k * k * cin * cout * N * h * w))
     ops.conv = timed_conv
+    multi = getattr(step.engine, "multi_stream", False)
+    step.engine.multi_stream = False        # per-launch times: one kernel at a time (the timed steps fork branches)
     try:
         load(batch)
         step._snapshot_and_restore(step._fwd_bwd)       # warm
@@ -331,6 +333,7 @@ def measure_rooflines(model, step, batch, load, pk, pk_src):
         torch.cuda.synchronize()
     finally:
         ops.conv = orig_conv
+        step.engine.multi_stream = multi
     tot_ms = sum(a.elapsed_time(b) for a, b, _ in recs)
     tot_fl = sum(f for _, _, f in recs)
     ach = tot_fl / (tot_ms * 1e-3) / 1e12
