@@ -33,6 +33,7 @@ struct WgArgs {
   float* dw;
   int N, H, W, cin, cout, cin_w, cout_w, k, pad;   // cin/cout padded to 16; *_w = real (dW extents)
   int dw_ci_stride;                                // Cin of the whole dW tensor (>= cin_w when this launch is a chunk)
+  int zb_ci, zb_co, tot_cin, tot_cout;             // blockIdx.z enumerates 256 x 256 blocks of a larger dW (1, 1: single block)
   int group;                                       // > 0: grouped conv chunk, dW is (Cout, group, k, k): only same-group entries are kept
   int nsplit;
   int x_is_m;                   // 1: M = X channels (Cin), N = G channels (Cout)
@@ -49,6 +50,18 @@ template <int MBLK, int NSPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const WgArgs p)
 {
+  // blockIdx.z = (Cout block, Cin block) of a dW larger than one launch's 256 x 256 limit: same tiling, shifted views
+  const int cob = (int)blockIdx.z / p.zb_ci, cib = (int)blockIdx.z - cob * p.zb_ci;
+  SrcView xv = p.x, gv = p.g;
+  int cin_w = p.cin_w, cout_w = p.cout_w;
+  float* dwp = p.dw;
+  if (p.zb_ci * p.zb_co > 1) {
+    const int ci0 = cib * 256, co0 = cob * 256;
+    xv.c0 += ci0; xv.dy_c0 += ci0; gv.c0 += co0; gv.dy_c0 += co0;       // (chunked launches require gap-free views)
+    cin_w = min(256, p.tot_cin - ci0); cout_w = min(256, p.tot_cout - co0);
+    xv.cvalid = (cin_w + 3) & ~3; gv.cvalid = (cout_w + 3) & ~3;
+    dwp += ((size_t)co0 * p.dw_ci_stride + ci0) * p.k * p.k;
+  }
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stages = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)p.nstages * p.stage_bytes);
@@ -58,8 +71,8 @@ wgrad_tc_kernel(const WgArgs p)
   uint32_t* tmem_base_sh = reinterpret_cast<uint32_t*>(bars + 5);
   float* xparams = reinterpret_cast<float*>(bars + 16);           // per-channel constants of X (5 x cin) then G (5 x cout)
   float* gparams = xparams + 5 * p.cin;
-  fillns::stage_params(p.x, xparams, p.cin, threadIdx.x, kThreads);
-  fillns::stage_params(p.g, gparams, p.cout, threadIdx.x, kThreads);
+  fillns::stage_params(xv, xparams, p.cin, threadIdx.x, kThreads);
+  fillns::stage_params(gv, gparams, p.cout, threadIdx.x, kThreads);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int group = blockIdx.y, slab = blockIdx.x;
@@ -146,8 +159,8 @@ wgrad_tc_kernel(const WgArgs p)
       const int oy = ty * p.TH, ox = tx * TW;
       uint8_t* xs = stages + (size_t)st * p.stage_bytes;
       uint8_t* gs = xs + p.x_bytes;
-      fillns::fill_window<kProducerThreads>(p.x, xs, p.x_plane, x_lo, p.nsplit, n, p.H, p.W, oy + ky0 - p.pad, ox - p.pad, p.xHP, p.xWP, 0, p.x_chunks, tid, xparams, p.cin);
-      fillns::fill_window<kProducerThreads>(p.g, gs, p.g_plane, g_lo, p.nsplit, n, p.H, p.W, oy, ox, p.TH, TW, 0, p.g_chunks, tid, gparams, p.cout);
+      fillns::fill_window<kProducerThreads>(xv, xs, p.x_plane, x_lo, p.nsplit, n, p.H, p.W, oy + ky0 - p.pad, ox - p.pad, p.xHP, p.xWP, 0, p.x_chunks, tid, xparams, p.cin);
+      fillns::fill_window<kProducerThreads>(gv, gs, p.g_plane, g_lo, p.nsplit, n, p.H, p.W, oy, ox, p.TH, TW, 0, p.g_chunks, tid, gparams, p.cout);
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&full[st]);
     }
@@ -172,9 +185,9 @@ wgrad_tc_kernel(const WgArgs p)
             for (int i = 0; i < 16; ++i) {
               const int nn = c16 + i;
               const int ci = p.x_is_m ? m : nn, co = p.x_is_m ? nn : m;
-              if (ci < p.cin_w && co < p.cout_w) {
-                if (p.group == 0) atomicAdd(p.dw + ((size_t)co * p.dw_ci_stride + ci) * kk + tap, v[i]);
-                else if (ci / p.group == co / p.group) atomicAdd(p.dw + ((size_t)co * p.group + ci % p.group) * kk + tap, v[i]);
+              if (ci < cin_w && co < cout_w) {
+                if (p.group == 0) atomicAdd(dwp + ((size_t)co * p.dw_ci_stride + ci) * kk + tap, v[i]);
+                else if (ci / p.group == co / p.group) atomicAdd(dwp + ((size_t)co * p.group + ci % p.group) * kk + tap, v[i]);
               }
             }
           }
@@ -203,15 +216,9 @@ SrcView make_view(const cvd_src_t* s, int cvalid) {
 int cvd_conv_wgrad_kx(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oihw,
                       int N, int H, int W, int cin, int cout, int k, int precision, void* stream);   // conv_wgrad_kx.cu
 
-// logical sub-range [s, ...) of a source view (x and dy views alike)
-static void sub_view(int& c_off, int& n0, int& gap, int s)
-{
-  if (gap != 0 && s >= n0) { c_off += s + gap; n0 = 0; gap = 0; }
-  else { c_off += s; if (gap != 0) n0 -= s; }
-}
-
 static int wgrad_impl(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oihw,
-                      int N, int H, int W, int cin, int cout, int k, int precision, int dw_ci_stride, void* stream, int group = 0);
+                      int N, int H, int W, int cin, int cout, int k, int precision, int dw_ci_stride, void* stream, int group = 0,
+                      int tot_cin = 0, int tot_cout = 0);
 
 extern "C" int cvd_conv_wgrad_grouped(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_ogkk,
                                       int N, int H, int W, int c, int group_size, int k, int precision, void* stream)
@@ -226,24 +233,20 @@ extern "C" int cvd_conv_wgrad(const cvd_src_t* gsrc, const cvd_src_t* xsrc, floa
 {
   CVD_CHECK_ARG(gsrc && xsrc && dw_oihw && gsrc->x && xsrc->x, "cvd_conv_wgrad: null pointer");
   if (cin > 256 || cout > 256) {
-    // channel counts above one launch's limits: 256 x 256 blocks of dW, operands read through sub-views
-    for (int co0 = 0; co0 < cout; co0 += 256)
-      for (int ci0 = 0; ci0 < cin; ci0 += 256) {
-        cvd_src_t g = *gsrc, x = *xsrc;
-        sub_view(g.c_off, g.n0, g.gap, co0); sub_view(g.dy_coff, g.dy_n0, g.dy_gap, co0);
-        sub_view(x.c_off, x.n0, x.gap, ci0); sub_view(x.dy_coff, x.dy_n0, x.dy_gap, ci0);
-        const int rc = wgrad_impl(&g, &x, dw_oihw + ((size_t)co0 * cin + ci0) * k * k, N, H, W,
-                                  cin - ci0 < 256 ? cin - ci0 : 256, cout - co0 < 256 ? cout - co0 : 256, k, precision,
-                                  cin, stream);
-        if (rc) return rc;
-      }
-    return 0;
+    // channel counts above one launch's limits: ONE launch whose blockIdx.z enumerates the 256 x 256 blocks of dW
+    // (operands read through shifted views); the pixel tiles are split over fewer slabs so the grid still fills the GPU
+    // and each dW element receives fewer RED contributions
+    CVD_CHECK_ARG(gsrc->gap == 0 && xsrc->gap == 0 && gsrc->dy_gap == 0 && xsrc->dy_gap == 0,
+                  "cvd_conv_wgrad: channel counts above 256 need gap-free views");
+    return wgrad_impl(gsrc, xsrc, dw_oihw, N, H, W, cin < 256 ? cin : 256, cout < 256 ? cout : 256, k, precision,
+                      cin, stream, 0, cin, cout);
   }
   return wgrad_impl(gsrc, xsrc, dw_oihw, N, H, W, cin, cout, k, precision, cin, stream);
 }
 
 static int wgrad_impl(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oihw,
-                      int N, int H, int W, int cin, int cout, int k, int precision, int dw_ci_stride, void* stream, int group)
+                      int N, int H, int W, int cin, int cout, int k, int precision, int dw_ci_stride, void* stream, int group,
+                      int tot_cin, int tot_cout)
 {
   CVD_CHECK_ARG(precision == 1 || precision == 3, "cvd_conv_wgrad: precision must be 1 or 3");
   CVD_CHECK_ARG(k >= 1 && k <= 11 && (k & 1), "cvd_conv_wgrad: k=%d unsupported", k);
@@ -262,6 +265,10 @@ static int wgrad_impl(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oi
   p.dw = dw_oihw; p.N = N; p.H = H; p.W = W; p.k = k; p.pad = (k - 1) / 2;
   p.cin_w = cin; p.cout_w = cout; p.cin = round_up(cin, 16); p.cout = round_up(cout, 16);
   p.dw_ci_stride = dw_ci_stride; p.group = group;
+  p.tot_cin = tot_cin > 0 ? tot_cin : cin; p.tot_cout = tot_cout > 0 ? tot_cout : cout;
+  p.zb_ci = (p.tot_cin + 255) / 256; p.zb_co = (p.tot_cout + 255) / 256;
+  if (tot_cin <= 0) { p.zb_ci = 1; p.zb_co = 1; }
+  const int zb = p.zb_ci * p.zb_co;
   p.nsplit = precision;
   CVD_CHECK_ARG(p.cin <= 256 && p.cout <= 256, "cvd_conv_wgrad: channel counts above 256 unsupported");
   p.x_is_m = p.cin >= p.cout;
@@ -297,7 +304,7 @@ static int wgrad_impl(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oi
   // lo planes start after the REAL chunk planes; the padded M reads may run into them (garbage rows, ignored)
   p.tiles_x = (W + TW - 1) / TW; p.tiles_y = (H + TH - 1) / TH;
   p.ntiles = N * p.tiles_x * p.tiles_y;
-  int slabs = (cvd_num_sms() + p.ngroups - 1) / p.ngroups;
+  int slabs = (cvd_num_sms() + p.ngroups * zb - 1) / (p.ngroups * zb);
   if (slabs > p.ntiles) slabs = p.ntiles;
   if (slabs < 1) slabs = 1;
   p.nslabs = slabs;
@@ -313,7 +320,7 @@ static int wgrad_impl(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oi
       e = cudaFuncSetAttribute(wgrad_tc_kernel<MB, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)); \
       cfg = true;                                                                                             \
     }                                                                                                         \
-    if (e == cudaSuccess) wgrad_tc_kernel<MB, NS><<<dim3(p.nslabs, p.ngroups), kThreads, smem, (cudaStream_t)stream>>>(p); \
+    if (e == cudaSuccess) wgrad_tc_kernel<MB, NS><<<dim3(p.nslabs, p.ngroups, zb), kThreads, smem, (cudaStream_t)stream>>>(p); \
   } while (0)
   if (p.mblk == 1) { if (precision == 3) CVD_WG_LAUNCH(1, 3); else CVD_WG_LAUNCH(1, 1); }
   else             { if (precision == 3) CVD_WG_LAUNCH(2, 3); else CVD_WG_LAUNCH(2, 1); }

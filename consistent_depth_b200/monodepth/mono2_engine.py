@@ -129,8 +129,8 @@ class _Act:
         return acc
 
 
-def _plain(t, C=None):
-    """cvd_src_t reading tensor t (N,h,w,Ct) as is (logical channels [0, C))."""
+def _plain(t):
+    """cvd_src_t reading tensor t (N,h,w,C) as is."""
     return ops.make_src(ops.View(t, 0))
 
 
@@ -152,9 +152,9 @@ class Mono2Engine:
     def _packed(self, cin, cout, k):
         return torch.empty(ops.packed_bytes(cin, cout, k, self.prec), dtype=torch.uint8, device=self.dev)
 
-    def _conv(self, src, wkey, bias_key, dst, cin, cout, k, h, w, bn=None, stats_of=None):
-        """Forward conv src -> dst (tensor, plain).  bn: _BN whose train-mode statistics are fused into the epilogue.
-        stats_of: (_BN, tensor) for a separate statistics pass (stride-2 convs: statistics of the picked pixels)."""
+    def _conv(self, src, wkey, bias_key, dst, cin, cout, k, h, w, bn=None):
+        """Forward conv src -> dst (tensor, plain).  bn: _BN whose train-mode statistics are fused into the epilogue
+        (stride-2 convs take theirs from cvd_bn_stats after the pick instead: _bn_stats)."""
         Wt = self._p(wkey)
         bias = self._p(bias_key) if bias_key else None
         pk = self._packed(cin, cout, k)

@@ -65,3 +65,31 @@ def test_registry_surface():
     from consistent_depth_b200.monodepth.midas_v2_model import MidasV2Model
     assert get_depth_model("midas2") is MidasV2Model
     assert (MidasV2Model.align, MidasV2Model.learning_rate, MidasV2Model.lambda_view_baseline) == (32, 0.0001, 0.0001)
+
+
+@pytest.mark.parametrize("model_type,H,W,lr,lam_b", [("monodepth2", 32, 48, 0.00004, 1), ("midas2", 64, 96, 0.0001, 0.0001)])
+def test_fine_tune_end_to_end_other_backbones(tmp_path, model_type, H, W, lr, lam_b):
+    """The same DepthFineTuner run with the other two registered model types (params.py:110-119 defaults, validation
+    passes, CUDA-graph steps, checkpoints where the reference writes them, depth export)."""
+    from consistent_depth_b200.depth_fine_tuning import DepthFineTuner
+    from consistent_depth_b200.synthetic_dataset import write_synthetic_dataset
+    from consistent_depth_b200.utils import image_io
+    root, range_dir = str(tmp_path / "clip"), str(tmp_path / "clip" / f"R0-4_hierarchical2_{model_type}")
+    n = 4
+    write_synthetic_dataset(root, range_dir, n, H, W, pairs=[(0, 1), (1, 2), (2, 3), (0, 2)])
+    params = make_params(root, model_type=model_type, num_epochs=1)
+    ft = DepthFineTuner(range_dir, list(range(n)), params)
+    assert params.learning_rate == lr and params.lambda_view_baseline == lam_b
+    w0 = ft.model.P.flat.clone()
+    ft.fine_tune(writer=None)
+    assert (ft.model.P.flat - w0).abs().max().item() > 0
+    ck = os.path.join(ft.out_dir, "checkpoints", "0001.pth")
+    if model_type == "monodepth2":
+        assert not os.path.exists(ck)                              # Monodepth2Model.save is a no-op (monodepth2_model.py:92-93)
+    else:
+        assert len(torch.load(ck, map_location="cpu")) == 666      # MidasNet.state_dict()
+    losses = json.load(open(os.path.join(ft.out_dir, "eval", "loss_e0001_iter000004.json")))
+    assert len(losses["reprojection"]) == 4 and all(np.isfinite(v) for v in losses["mean"].values())
+    ft.save_depth()
+    d1 = image_io.load_raw_float32_image(os.path.join(ft.out_dir, "depth", "frame_000001.raw"))
+    assert d1.shape == (H, W) and np.isfinite(d1).all() and (d1 > 0).all()
