@@ -522,10 +522,16 @@ static int conv_fwd_impl(const cvd_src_t* src, const void* packed_w, const float
   const int smem_budget = 212 * 1024;
   const int cand[6][2] = {{4, 2}, {4, 1}, {2, 2}, {2, 1}, {1, 2}, {1, 1}};   // (mtx, mty), largest first
   bool found = false;
+  // Grid fill: a persistent CTA owns whole tiles, so on small feature maps the largest tile leaves most SMs idle
+  // (28x48x8 frames in 32x32-pixel tiles = 16 CTAs).  Prefer the largest tile that still yields >= one tile per SM,
+  // then relax the requirement step by step (CVD_TILE_FILL=0 restores "largest tile that fits").
+  static const bool fill_grid = !(getenv("CVD_TILE_FILL") && getenv("CVD_TILE_FILL")[0] == '0');
+  for (int min_tiles = fill_grid ? cvd_num_sms() : 0; !found; min_tiles = min_tiles > 8 ? min_tiles / 2 : 0) {
   for (int want_slots = 2; want_slots >= 1 && !found; --want_slots) {
     for (int ci = 0; ci < 6 && !found; ++ci) {
       const int mtx = cand[ci][0], mty = cand[ci][1];
       if (2 * mtx * mty * p.cout > 512) continue;
+      if ((long long)N * ((W + 8 * mtx - 1) / (8 * mtx)) * ((H + 16 * mty - 1) / (16 * mty)) < min_tiles) continue;
       if (8 * mtx > round_up(W, 8) && mtx > 1) continue;
       if (16 * mty > round_up(H, 16) && mty > 1) continue;
       const int HP = 16 * mty + k - 1, WP = 8 * mtx + k - 1;
@@ -556,6 +562,8 @@ static int conv_fwd_impl(const cvd_src_t* src, const void* packed_w, const float
         }
       }
     }
+  }
+    if (min_tiles == 0) break;
   }
   CVD_CHECK_ARG(found, "cvd_conv_fwd: no tile fits shared memory (cin=%d cout=%d k=%d)", cin, cout, k);
   p.tiles_x = (W + 8 * p.mtx - 1) / (8 * p.mtx);
