@@ -17,6 +17,7 @@ from torch.utils.data import DataLoader
 from . import optimizer
 from .distributed import global_focal, shard_slice
 from .fine_tune_step import FineTuneStep
+from .loaders.resident import ResidentLoader, ResidentVideoDataset
 from .loaders.video_dataset import VideoDataset, VideoFrameDataset
 from .loss.joint_loss import JointLoss
 from .loss.loss_params import LossParams
@@ -91,8 +92,15 @@ class DepthFineTuner:
         B_global = P.batch_size
         B_local = B_global // self.world
         gen = torch.Generator().manual_seed(0)              # same shuffle on every rank; ranks take disjoint slices
-        train_loader = DataLoader(dataset, batch_size=B_global, shuffle=True, num_workers=4, pin_memory=pin, generator=gen)
-        val_loader = DataLoader(dataset, batch_size=B_local, shuffle=False, num_workers=4, pin_memory=pin)
+        if getattr(P, "resident_dataset", True):
+            # the whole clip lives in HBM (340 MB at 224x384 / 50 frames); same batches in the same order
+            # as the DataLoader below (tests/test_resident_loader_cpu.py), no per-step file reads, PNG decodes or H2D copies
+            resident = ResidentVideoDataset(dataset, self.model.device_)
+            train_loader = ResidentLoader(resident, B_global, shuffle=True, generator=gen)
+            val_loader = ResidentLoader(resident, B_local, shuffle=False)
+        else:
+            train_loader = DataLoader(dataset, batch_size=B_global, shuffle=True, num_workers=4, pin_memory=pin, generator=gen)
+            val_loader = DataLoader(dataset, batch_size=B_local, shuffle=False, num_workers=4, pin_memory=pin)
         criterion = JointLoss(P)
         eval_dir = pjoin(self.out_dir, "eval")
         os.makedirs(eval_dir, exist_ok=True)

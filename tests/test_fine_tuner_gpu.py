@@ -21,7 +21,8 @@ def make_params(root, **kw):
     return p
 
 
-def test_fine_tune_and_save_depth_end_to_end(tmp_path):
+@pytest.mark.parametrize("resident", [True, False])
+def test_fine_tune_and_save_depth_end_to_end(tmp_path, resident):
     from consistent_depth_b200.depth_fine_tuning import DepthFineTuner, make_tag
     from consistent_depth_b200.monodepth import mc_arch
     from consistent_depth_b200.synthetic_dataset import write_synthetic_dataset
@@ -29,7 +30,7 @@ def test_fine_tune_and_save_depth_end_to_end(tmp_path):
     root, range_dir = str(tmp_path / "clip"), str(tmp_path / "clip" / "R0-4_hierarchical2_mc")
     H, W, n = 32, 48, 4
     write_synthetic_dataset(root, range_dir, n, H, W, pairs=[(0, 1), (1, 2), (2, 3), (0, 2)])
-    params = make_params(root)
+    params = make_params(root, resident_dataset=resident)     # HBM-resident clip (default) or the reference's file DataLoader
     ft = DepthFineTuner(range_dir, list(range(n)), params)
     # params.py:110-119 semantics: sentinels resolved from the model class
     assert params.learning_rate == 0.0004 and params.lambda_view_baseline == 0.1
