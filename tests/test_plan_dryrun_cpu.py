@@ -1,0 +1,99 @@
+"""CPU: the static execution plans of the monodepth2 and MiDaS engines, built and replayed against a recording stand-in
+for the C-ABI library (no kernels run).  Checks the host-side plumbing that a GPU is not needed for: the plan builds for
+the fixture shapes, forward / backward / eval replay without Python errors, every conv of the architecture table is
+launched, and every trainable conv weight receives a weight-gradient launch whose destination is that tensor's slice of
+the flat gradient buffer (grouped / >256-channel convs: all their chunks)."""
+import collections
+import ctypes as C
+
+import pytest
+import torch
+
+
+class _Recorder:
+    def __init__(self, real):
+        self.real, self.calls, self.args = real, collections.Counter(), collections.defaultdict(list)
+
+    def __getattr__(self, name):
+        if name in ("cvd_bn_scratch_bytes", "cvd_conv_packed_bytes"):
+            return getattr(self.real, name)
+
+        def f(*a):
+            self.calls[name] += 1
+            self.args[name].append(a)
+            return 0
+        return f
+
+
+@pytest.fixture
+def fake_lib(monkeypatch):
+    from consistent_depth_b200 import _lib
+    rec = _Recorder(_lib.lib())
+    monkeypatch.setattr(_lib, "lib", lambda: rec)
+    monkeypatch.setattr(_lib, "ptr", lambda t: C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr()))
+    monkeypatch.setattr(_lib, "stream", lambda: C.c_void_p(0))
+    monkeypatch.setenv("CVD_MULTI_STREAM", "0")
+    return rec
+
+
+def _wgrad_targets(rec):
+    out = collections.Counter()
+    for name in ("cvd_conv_wgrad", "cvd_conv_wgrad_grouped"):
+        for a in rec.args[name]:
+            out[a[2].value] += 1
+    return out
+
+
+def _check_weight_coverage(P, arch, rec, chunk_rows=None):
+    targets = _wgrad_targets(rec)
+    for k, (off, shape) in P.pmap.items():
+        if len(shape) != 4 or arch.dead_parameter(k):
+            continue
+        g = P._g(k)
+        if chunk_rows and shape[1] * 32 == shape[0]:            # grouped (Cout, Cout/32, 3, 3): one launch per 64 output rows
+            rows = range(0, shape[0], chunk_rows)
+            assert all(targets[g[r:r + 1].data_ptr()] == 1 for r in rows), k
+        else:
+            assert targets[g.data_ptr()] == 1, k
+    dead = [P._g(k).data_ptr() for k in P.pmap if arch.dead_parameter(k)]
+    assert not any(targets[p] for p in dead)
+
+
+def test_monodepth2_plan(fake_lib):
+    from consistent_depth_b200.monodepth import mono2_arch
+    from consistent_depth_b200.monodepth.mono2_engine import Mono2Engine, Mono2Params
+    P = Mono2Params("cpu")
+    e = Mono2Engine(P, 2, 24, 40, (64, 96))
+    depth = e.forward(torch.rand(2, 3, 24, 40))
+    assert depth.shape == (2, 24, 40)
+    n_convs = sum(1 for k, s in mono2_arch.state_dict_shapes().items() if len(s) == 4 and not mono2_arch.dead_parameter(k))
+    assert n_convs == 31 and fake_lib.calls["cvd_conv_fwd"] + fake_lib.calls["cvd_conv_fwd_bn"] == n_convs
+    assert fake_lib.calls["cvd_conv_fwd_bn"] == 16           # stride-1 convs followed by BatchNorm: statistics in the epilogue
+    assert fake_lib.calls["cvd_bn_stats"] == 4               # the four stride-2 convs followed by BatchNorm
+    e.backward(torch.rand(2, 24, 40))
+    assert fake_lib.calls["cvd_conv_wgrad"] == n_convs and fake_lib.calls["cvd_bn_bwd_reduce"] == 20
+    assert fake_lib.calls["cvd_conv_fwd"] + fake_lib.calls["cvd_conv_fwd_bn"] == 2 * n_convs - 1    # no dgrad into the image
+    _check_weight_coverage(P, mono2_arch, fake_lib)
+    e.train_mode = False
+    fake_lib.calls.clear()
+    e.forward(torch.rand(2, 3, 24, 40))
+    assert fake_lib.calls["cvd_conv_fwd_bn"] == 0 and fake_lib.calls["cvd_bn_stats"] == 0            # eval: running statistics
+    assert P.num_batches_tracked == 1
+
+
+def test_midas_plan(fake_lib):
+    from consistent_depth_b200.monodepth import midas_arch
+    from consistent_depth_b200.monodepth.midas_engine import CHUNK, MidasEngine, MidasParams
+    P = MidasParams("cpu")
+    e = MidasEngine(P, 2, 64, 96)
+    assert e.forward(torch.rand(2, 3, 64, 96)).shape == (2, 64, 96)
+    shapes = midas_arch.state_dict_shapes()
+    dense = [k for k, s in shapes.items() if len(s) == 4 and not midas_arch.dead_parameter(k) and s[1] * 32 != s[0]]
+    grouped = [k for k, s in shapes.items() if len(s) == 4 and s[1] * 32 == s[0]]
+    chunks = sum(shapes[k][0] // CHUNK for k in grouped)
+    assert len(grouped) == 33 and chunks == 508
+    assert fake_lib.calls["cvd_conv_fwd"] + fake_lib.calls["cvd_conv_fwd_bn"] == len(dense) + chunks
+    e.backward(torch.rand(2, 64, 96))
+    assert fake_lib.calls["cvd_conv_wgrad"] == len(dense) and fake_lib.calls["cvd_conv_wgrad_grouped"] == chunks
+    assert fake_lib.calls["cvd_bn_bwd_reduce"] == 104                                              # 104 BatchNorms
+    _check_weight_coverage(P, midas_arch, fake_lib, chunk_rows=CHUNK)
