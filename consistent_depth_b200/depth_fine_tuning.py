@@ -109,15 +109,16 @@ class DepthFineTuner:
         H, W = images0.shape[-2:]
         steps = {}
 
-        def get_step(b):
-            if b not in steps:
-                steps[b] = FineTuneStep(self.model, b, H, W, lr=P.learning_rate, lambda_reprojection=P.lambda_reprojection,
-                                        lambda_view_baseline=P.lambda_view_baseline, world_size=self.world)
-                if steps:
-                    first = next(iter(steps.values()))           # all batch shapes share ONE Adam state
-                    s = steps[b]
+        def get_step(b, b_global):
+            key = (b, b_global)
+            if key not in steps:
+                first = next(iter(steps.values())) if steps else None
+                steps[key] = FineTuneStep(self.model, b, H, W, lr=P.learning_rate, lambda_reprojection=P.lambda_reprojection,
+                                          lambda_view_baseline=P.lambda_view_baseline, world_size=self.world, B_global=b_global)
+                if first is not None:                            # all batch shapes share ONE Adam state
+                    s = steps[key]
                     s.exp_avg, s.exp_avg_sq, s.adam_state = first.exp_avg, first.exp_avg_sq, first.adam_state
-            return steps[b]
+            return steps[key]
 
         def validate(epoch, niters):
             meta = self.eval_and_save(criterion, val_loader, f"_e{epoch:04d}_iter{niters:06d}")
@@ -134,14 +135,15 @@ class DepthFineTuner:
             t0 = time.perf_counter()
             for images, metadata in train_loader:
                 nb = images.shape[0]
-                if nb % self.world:                              # ragged last batch: drop the remainder pairs
-                    nb -= nb % self.world
-                    if nb == 0:
-                        continue
-                bl = nb // self.world
-                sl = shard_slice(nb, self.rank, self.world)
+                sl = shard_slice(nb, self.rank, self.world)      # ragged last batch: uneven shares, possibly none
+                bl = sl.stop - sl.start
                 geom = metadata["geometry_consistency"]
-                step = get_step(bl)
+                if bl == 0:
+                    loss = next(iter(steps.values())).step_empty()
+                    pending = (epoch, geom["indices"][:nb].tolist(), loss.clone())
+                    total_iters += nb
+                    continue
+                step = get_step(bl, nb)
                 f_dir = None
                 if self.world > 1:
                     f_dir = global_focal(metadata["intrinsics"], nb)

@@ -10,9 +10,12 @@ import torch
 
 
 def shard_slice(n_pairs, rank, world):
-    """Contiguous slice of a global mini-batch of n_pairs owned by `rank` (n_pairs is first trimmed to a multiple of world)."""
-    per = n_pairs // world
-    return slice(rank * per, (rank + 1) * per)
+    """Contiguous slice of a global mini-batch of n_pairs owned by `rank`.  A ragged batch (the last one of an epoch:
+    138 pairs = 17 x 8 + 2) is split as evenly as possible, the first n_pairs % world ranks taking one extra pair; a
+    rank may own no pair at all (empty slice) -- it still joins the step's all-reduce with a zero contribution."""
+    per, extra = divmod(n_pairs, world)
+    start = rank * per + min(rank, extra)
+    return slice(start, start + per + (1 if rank < extra else 0))
 
 
 def global_focal(intrinsics, n_pairs=None):

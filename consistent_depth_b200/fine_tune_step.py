@@ -25,13 +25,14 @@ from .utils.geometry import _Workspace
 
 class FineTuneStep:
     def __init__(self, model, B_local, H, W, lr, lambda_reprojection=1.0, lambda_view_baseline=None,
-                 betas=(0.9, 0.999), eps=1e-8, world_size=1, process_group=None, use_graph=True):
+                 betas=(0.9, 0.999), eps=1e-8, world_size=1, process_group=None, use_graph=True, B_global=None):
         self.model, self.B, self.H, self.W = model, B_local, H, W
         self.lr, self.betas, self.eps = float(lr), betas, float(eps)
         self.lam_r = float(lambda_reprojection)
         self.lam_b = float(model.lambda_view_baseline if lambda_view_baseline is None else lambda_view_baseline)
         self.world, self.pg = world_size, process_group
-        self.B_global = B_local * world_size
+        # pairs of the GLOBAL mini-batch (the 1/B of consistency_loss.py:208); ranks may hold unequal shares of a ragged batch
+        self.B_global = B_local * world_size if B_global is None else int(B_global)
         dev = model.device_
         self.dev = dev
         self.engine = model.engine(2 * B_local, H, W)
@@ -144,6 +145,16 @@ class FineTuneStep:
         else:
             self._fwd_bwd()
         # ONE all-reduce over NVLink: [flat gradient | local loss (already divided by B_global)], in place
+        allreduce_flat(P.grad_store, self.pg)
+        self._adam(self.loss)
+        return self.loss
+
+    def step_empty(self):
+        """This rank owns no pair of the (ragged) global mini-batch: contribute zeros to the all-reduce, apply the same
+        Adam update as every other rank (the reduced loss drives the same NaN guard)."""
+        assert self.world > 1
+        P = self.model.P
+        P.grad_store.zero_()
         allreduce_flat(P.grad_store, self.pg)
         self._adam(self.loss)
         return self.loss

@@ -63,14 +63,17 @@ def test_two_rank_sharding_matches_single_process():
 
 
 def test_shard_slices_partition_the_batch():
+    """Even and ragged global batches (the last batch of 138 pairs at global batch 8 holds 2): contiguous, disjoint,
+    complete, sizes differ by at most one, ranks beyond the batch get an empty slice."""
     from consistent_depth_b200.distributed import shard_slice
     for world in (1, 2, 4, 8):
-        n = 8
-        seen = []
-        for r in range(world):
-            s = shard_slice(n, r, world)
-            seen += list(range(n))[s]
-        assert seen == list(range(n))
+        for n in (8, 2, 5, 1, 16, 7):
+            seen, sizes = [], []
+            for r in range(world):
+                s = shard_slice(n, r, world)
+                seen += list(range(n))[s]
+                sizes.append(s.stop - s.start)
+            assert seen == list(range(n)) and max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
 
 
 def test_pair_sampling_and_dataset_roundtrip(tmp_path):
