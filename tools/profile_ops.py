@@ -7,6 +7,7 @@ import sys
 
 import torch
 
+os.environ.setdefault("CVD_MULTI_STREAM", "0")     # per-op times: one kernel at a time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from consistent_depth_b200 import ops  # noqa: E402
 from consistent_depth_b200.fine_tune_step import FineTuneStep  # noqa: E402
@@ -37,7 +38,7 @@ def wrap(name, describe):
     setattr(ops, name, f)
 
 
-wrap("conv", lambda s, pk, bias, d, N, h, w, cin, cout, k, p=3, fl=0: (f"{'dgrad' if s.mode else 'fwd'} {cin}->{cout} k{k} {h}x{w}", 2.0 * k * k * cin * cout * N * h * w))
+wrap("conv", lambda s, pk, bias, d, N, h, w, cin, cout, k, p=3, fl=0, bn=None: (f"{'dgrad' if s.mode else 'fwd'} {cin}->{cout} k{k} {h}x{w}", 2.0 * k * k * cin * cout * N * h * w))
 wrap("conv_wgrad", lambda g, x, dw, N, h, w, cin, cout, k, p=3: (f"wgrad {cin}->{cout} k{k} {h}x{w}", 2.0 * k * k * cin * cout * N * h * w))
 wrap("bn_stats", lambda x, off, C, npix, *a, **k: (f"C{C} npix{npix}", 4.0 * C * npix))
 wrap("bn_bwd_reduce", lambda x, off, C, dy, npix, *a, **k: (f"C{C} npix{npix}", 8.0 * C * npix))
