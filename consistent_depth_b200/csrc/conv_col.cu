@@ -1,0 +1,523 @@
+// Rectangular-filter variant of the tcgen05 implicit-GEMM convolution (conv_tc.cu): kh x kw taps, separate
+// y / x paddings and an output that may be wider than the input.  EXPERIMENTAL, not on the default path.
+//
+// Purpose: the forward convs with few output channels (Cout = 16 / 32) are bound by the NUMBER of
+// N = 16 MMAs.  A k x k conv with Cout outputs equals a k x 1 (column) conv with k*Cout outputs
+//     D[y, x', kx*Cout + co] = sum_{ky, ci} X[y + ky - pad, x' - pad, ci] * W[co, ci, ky, kx]      (x' in [0, W + k - 1))
+// followed by the shifted sum  out[y, x, co] = sum_kx D[y, x + kx, kx*Cout + co]  (cvd_shift_sum, kx_epilogue.cu).
+// The column conv runs here with N = k*Cout (176 for 64->16 11x11): 11x fewer, 11x wider MMAs.
+//
+// This file is conv_tc.cu with the filter / padding / output-width generalisation applied and the pieces the
+// experiment does not need removed (dgrad packing, grouped weights, >256-column chunking, fused BN statistics);
+// it is kept separate until validated on hardware so that the production kernel stays byte-identical.
+// Enabled only by CVD_KXFWD=1 (mc_engine.py); tests: tests/test_kxfwd_gpu.py (opt-in, CVD_TEST_KXFWD=1).
+#include "cvd_common.cuh"
+#include "tc_common.cuh"
+#include "fill.cuh"
+
+namespace {
+
+constexpr int kIssuers = 2;                // MMA issuer warps (M-tiles split between them)
+constexpr int kThreads = 32 * (kIssuers + 1 + 8 + 4);   // issuers | weight streamer | 8 producer warps | 4 epilogue warps
+constexpr int kProducerThreads = 256;
+constexpr int kMaxStages = 8;
+constexpr int kGroupCh = 64;          // channels per activation group resident in one A slot
+
+struct ConvArgs {
+  fillns::SrcView src;               // source view + transform
+  // weights / bias
+  const uint8_t* wp; const float* bias;
+  // destination view
+  float* y; int y_ct, y_c0, y_n0, y_gap; int cout_valid;
+  // problem
+  int N, H, W, Wout, cin, cout, kh, kw, pad_y, pad_x;   // W: input width, Wout: output width (column conv: W + k - 1)
+  int flags, nsplit;                 // nsplit: 1 (bf16) or 3 (bf16x3)
+  // tiling
+  int mtx, mty, tiles_x, tiles_y;    // M-tiles per CTA along x / y
+  int HP, WP, plane_bytes;           // halo dims, bytes of one 8-channel plane (padded)
+  int slot_bytes, nslots, ngroups, gchunks;   // items per tile, chunks (8 ch) per item (max)
+  int gsplit;                                 // 1: an item = one 64-channel pack group; 2: half of it (32 ch)
+  int ntiles;
+  int stage_bytes, nstages, kbs, kb_bytes;    // a weight stage = kbs k-blocks of kb_bytes each
+  int tmem_cols;
+  // fused BatchNorm(train) statistics of the conv output (NULL scratch: off)
+  double* st_scratch; const float* st_gamma; const float* st_beta; float* st_rm; float* st_rv;
+  float* st_a; float* st_b; float* st_rstd; float* st_mean; float st_eps, st_mom; long long st_count;
+};
+
+__device__ __forceinline__ int view_phys(int c, int c0, int n0, int gap) { return c0 + c + (c >= n0 ? gap : 0); }
+
+// ------------------------------------------------------------------ the kernel
+template <int MT, int NSPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+convr_kernel(const ConvArgs p)
+{
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // layout: [A slots][B stages][barriers]
+  uint8_t* a_slots = smem;
+  uint8_t* b_stages = a_slots + (size_t)p.nslots * p.slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_stages + (size_t)p.nstages * p.stage_bytes);
+  uint64_t* b_full = bars;                       // [kMaxStages]
+  uint64_t* b_empty = bars + kMaxStages;         // [kMaxStages]
+  uint64_t* a_full = bars + 2 * kMaxStages;      // [2]
+  uint64_t* a_empty = a_full + 2;                // [2]
+  uint64_t* acc_full = a_empty + 2;              // [2]
+  uint64_t* acc_empty = acc_full + 2;            // [2]
+  uint32_t* tmem_base_sh = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sparams = reinterpret_cast<float*>(bars + 32);           // per-channel constants, 5 x cin floats
+  fillns::stage_params(p.src, sparams, p.cin, threadIdx.x, kThreads);
+  float* sstat = sparams + 5 * p.cin;                              // [4 epilogue warps][2][cout] column sums / sums of squares
+  if (p.st_scratch) for (int i = threadIdx.x; i < 8 * p.cout; i += kThreads) sstat[i] = 0.f;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.nstages; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], kIssuers); }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&a_full[i], kProducerThreads); tc::mbar_init(&a_empty[i], kIssuers);
+      tc::mbar_init(&acc_full[i], kIssuers); tc::mbar_init(&acc_empty[i], 4);
+    }
+    tc::mbar_fence_init();
+  }
+  if (warp == 0) {
+    tc::tmem_alloc_dyn(tmem_base_sh, (uint32_t)p.tmem_cols);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_sh;
+
+  const int taps = p.kh * p.kw;
+
+  // item i of a tile -> (pack group g64, sub-group h): channel range and k-block range inside the pack group
+  auto item_cfirst = [&](int it) { return p.gsplit == 2 ? (it >> 1) * kGroupCh + (it & 1) * 32 : it * kGroupCh; };
+  auto item_chunks = [&](int it) { return p.gsplit == 2 ? 4 : min(p.gchunks, (p.cin - it * kGroupCh) >> 3); };
+
+  if (warp < kIssuers) {
+    // ============================ MMA issuers ============================
+    // Two issuer warps, each owning half of the CTA's M-tiles (a single thread cannot issue the small-N MMAs
+    // fast enough; measured 1.5x on the wgrad kernel).  With one M-tile the second warp only keeps the protocol.
+    constexpr int MTW = MT >= kIssuers ? MT / kIssuers : MT;        // M-tiles per issuer warp
+    const int mt0 = MT >= kIssuers ? warp * MTW : 0;
+    const bool active = MT >= kIssuers || warp == 0;
+    const uint32_t idesc = tc::idesc_bf16(128, p.cout, 0, 0);
+    const uint32_t a_base = tc::smem_u32(a_slots), b_base = tc::smem_u32(b_stages);
+    const uint32_t lo_a = (uint32_t)p.gchunks * p.plane_bytes;      // hi -> lo plane offset inside a slot
+    const uint32_t lo_b = (uint32_t)p.cout * 32;                     // hi -> lo blob offset inside a k-block
+    const uint64_t adesc0 = tc::smem_desc_base((uint32_t)p.plane_bytes, (uint32_t)p.WP * 16);
+    const uint64_t bdesc0 = tc::smem_desc_base(128, 256);
+    uint32_t aoff[MTW];
+#pragma unroll
+    for (int i = 0; i < MTW; ++i) {
+      const int mt = mt0 + i;
+      const int my = mt / p.mtx, mx = mt - my * p.mtx;
+      aoff[i] = (uint32_t)((my * 16 * p.WP + mx * 8) * 16);
+    }
+    int stage = 0; uint32_t bphase = 0;
+    int item = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
+      const int buf = ti & 1;
+      if (ti >= 2) { tc::mbar_wait(&acc_empty[buf], (uint32_t)(((ti >> 1) - 1) & 1)); tc::tc_fence_after(); }
+      const uint32_t dbase = tmem_base + (uint32_t)(buf * MT * p.cout);
+      uint32_t first = 0u;
+      for (int g = 0; g < p.ngroups; ++g, ++item) {
+        const int slot = item % p.nslots;
+        tc::mbar_wait(&a_full[slot], (uint32_t)((item / p.nslots) & 1));
+        tc::tc_fence_after();
+        const uint32_t slot_addr = a_base + (uint32_t)slot * p.slot_bytes;
+        const int nks = (item_chunks(g) >> 1) / p.kbs;              // weight stages per tap for this item
+        for (int ky = 0; ky < p.kh; ++ky) {
+          uint32_t a_row = slot_addr + (uint32_t)(ky * p.WP * 16);
+          for (int kx = 0; kx < p.kw; ++kx, a_row += 16) {
+            for (int ks = 0; ks < nks; ++ks) {
+              tc::mbar_wait(&b_full[stage], bphase);
+              tc::tc_fence_after();
+              if (tc::elect_one()) {
+                uint32_t bs = b_base + (uint32_t)stage * p.stage_bytes;
+                uint32_t a_kb = a_row + (uint32_t)(2 * ks * p.kbs) * p.plane_bytes;
+                for (int j = 0; j < p.kbs && active; ++j, bs += p.kb_bytes, a_kb += 2 * p.plane_bytes) {
+                  const uint64_t bd_hi = tc::smem_desc_at(bdesc0, bs), bd_lo = tc::smem_desc_at(bdesc0, bs + lo_b);
+#pragma unroll
+                  for (int i = 0; i < MTW; ++i) {
+                    const uint32_t d = dbase + (uint32_t)((mt0 + i) * p.cout);
+                    const uint64_t ad_hi = tc::smem_desc_at(adesc0, a_kb + aoff[i]);
+                    tc::umma_f16(d, ad_hi, bd_hi, idesc, first);
+                    if (NSPLIT == 3) {
+                      tc::umma_f16(d, tc::smem_desc_at(adesc0, a_kb + aoff[i] + lo_a), bd_hi, idesc, 1u);
+                      tc::umma_f16(d, ad_hi, bd_lo, idesc, 1u);
+                    }
+                  }
+                  first = 1u;
+                }
+                tc::umma_commit(&b_empty[stage]);        // weight stage reusable once these MMAs retire
+              }
+              __syncwarp();
+              first = 1u;
+              if (++stage == p.nstages) { stage = 0; bphase ^= 1; }
+            }
+          }
+        }
+        if (tc::elect_one()) tc::umma_commit(&a_empty[slot]);   // activation slot reusable
+        __syncwarp();
+      }
+      if (tc::elect_one()) tc::umma_commit(&acc_full[buf]);     // this tile's accumulators complete
+      __syncwarp();
+    }
+  } else if (warp == kIssuers) {
+    // ============================ weight streamer ============================
+    if (lane == 0) {
+      int stage = 0; uint32_t ephase = 0; long long issued = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        for (int g = 0; g < p.ngroups; ++g) {
+          const int g64 = p.gsplit == 2 ? (g >> 1) : g;
+          const int kbg = min(kGroupCh, p.cin - g64 * kGroupCh) >> 4;       // k-blocks of the pack group
+          const int kb0 = p.gsplit == 2 ? (g & 1) * 2 : 0;                  // first k-block of this item
+          const int nks = (item_chunks(g) >> 1) / p.kbs;
+          const uint8_t* gsrc = p.wp + (size_t)g64 * taps * (kGroupCh / 16) * p.kb_bytes;
+          for (int tap = 0; tap < taps; ++tap) {
+            for (int ks = 0; ks < nks; ++ks, ++issued) {
+              if (issued >= p.nstages) {
+                tc::mbar_wait(&b_empty[stage], ephase);
+              }
+              const uint8_t* src = gsrc + (size_t)(tap * kbg + kb0 + ks * p.kbs) * p.kb_bytes;
+              tc::mbar_arrive_expect_tx(&b_full[stage], (uint32_t)p.stage_bytes);
+              tc::bulk_g2s(b_stages + (size_t)stage * p.stage_bytes, src, (uint32_t)p.stage_bytes, &b_full[stage]);
+              if (++stage == p.nstages) { stage = 0; if (issued >= p.nstages) ephase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < kIssuers + 9) {
+    // ============================ activation producers ============================
+    const int tid = threadIdx.x - 32 * (kIssuers + 1);
+    int item = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      int t = tile;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; const int n = t / p.tiles_y;
+      const int ox = tx * (8 * p.mtx), oy = ty * (16 * p.mty);
+      for (int g = 0; g < p.ngroups; ++g, ++item) {
+        const int slot = item % p.nslots;
+        if (item >= p.nslots) tc::mbar_wait(&a_empty[slot], (uint32_t)(((item / p.nslots) - 1) & 1));
+        fillns::fill_window<kProducerThreads>(p.src, a_slots + (size_t)slot * p.slot_bytes, p.plane_bytes, p.gchunks * p.plane_bytes, p.nsplit,
+                            n, p.H, p.W, oy - p.pad_y, ox - p.pad_x, p.HP, p.WP, item_cfirst(g), item_chunks(g), tid, sparams, p.cin);
+        tc::fence_proxy_async_smem();
+        tc::mbar_arrive(&a_full[slot]);
+      }
+    }
+  } else {
+    // ============================ epilogue ============================
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;                   // accumulator row = pixel inside the M-tile
+    const int py = row >> 3, px = row & 7;
+    const bool accum = (p.flags & 1) != 0, do_exp = (p.flags & 2) != 0;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
+      int t = tile;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; const int n = t / p.tiles_y;
+      const int ox = tx * (8 * p.mtx), oy = ty * (16 * p.mty);
+      const int buf = ti & 1;
+      tc::mbar_wait(&acc_full[buf], (uint32_t)((ti >> 1) & 1));
+      tc::tc_fence_after();
+      for (int mt = 0; mt < MT; ++mt) {
+        const int my = mt / p.mtx, mx = mt - my * p.mtx;
+        const int yy = oy + my * 16 + py, xx = ox + mx * 8 + px;
+        const bool inside = yy < p.H && xx < p.Wout;
+        float* yp = p.y + (((size_t)n * p.H + (inside ? yy : 0)) * p.Wout + (inside ? xx : 0)) * p.y_ct;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * MT + mt) * p.cout);
+        for (int c16 = 0; c16 < p.cout; c16 += 16) {
+          float v[16];
+          tc::tmem_ld16(taddr + (uint32_t)c16, v);    // warp-collective: executed by all lanes
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (c16 + i < p.cout_valid) v[i] += __ldg(p.bias + c16 + i);
+          }
+          if (p.st_scratch) {
+            // BatchNorm batch statistics fused into the epilogue: column sums over the warp's 32 pixels by a
+            // transposing butterfly (8+4+2+1+1 shuffles per quantity), accumulated per warp in shared memory.
+            float sv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sv[i] = inside ? v[i] : 0.f;
+            float tot[2];
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq) {
+              float t8[8], t4[4], t2[2];
+              const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float lo_ = qq ? sv[i] * sv[i] : sv[i], hi_ = qq ? sv[8 + i] * sv[8 + i] : sv[8 + i];
+                t8[i] = (b4 ? hi_ : lo_) + __shfl_xor_sync(0xffffffffu, b4 ? lo_ : hi_, 16);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) t4[i] = (b3 ? t8[4 + i] : t8[i]) + __shfl_xor_sync(0xffffffffu, b3 ? t8[i] : t8[4 + i], 8);
+#pragma unroll
+              for (int i = 0; i < 2; ++i) t2[i] = (b2 ? t4[2 + i] : t4[i]) + __shfl_xor_sync(0xffffffffu, b2 ? t4[i] : t4[2 + i], 4);
+              const float t1 = (b1 ? t2[1] : t2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? t2[0] : t2[1], 2);
+              tot[qq] = t1 + __shfl_xor_sync(0xffffffffu, t1, 1);
+            }
+            if (!(lane & 1)) {                           // 16 lanes hold the 16 distinct columns of this chunk
+              const int col = c16 + ((lane >> 1) & 1) + ((lane >> 2) & 1) * 2 + ((lane >> 3) & 1) * 4 + ((lane >> 4) & 1) * 8;
+              float* ws = sstat + (size_t)q * 2 * p.cout;
+              ws[col] += tot[0]; ws[p.cout + col] += tot[1];
+            }
+          }
+          if (!inside || c16 >= p.cout_valid) continue;
+          if (do_exp) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = expf(v[i]);
+          }
+          float* dst = yp + view_phys(c16, p.y_c0, p.y_n0, p.y_gap);
+          if (c16 + 16 <= p.cout_valid) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              if (accum) { const float4 old = *reinterpret_cast<const float4*>(dst + i); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+              *reinterpret_cast<float4*>(dst + i) = o;
+            }
+          } else {
+            for (int i = 0; i < p.cout_valid - c16; ++i) dst[i] = accum ? dst[i] + v[i] : v[i];
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);   // accumulator buffer free for tile ti + 2
+    }
+    if (p.st_scratch) {
+      // CTA partials -> f64 atomics; the last CTA (ticket) finalises a = gamma*rstd, b = beta - mean*a and the
+      // running statistics exactly as bn_stats_kernel does (hourglass.py:28,40,43,165, train mode)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int et = threadIdx.x - 32 * (kIssuers + 9);
+      for (int c = et; c < p.cout_valid; c += 128) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { s1 += sstat[(size_t)w * 2 * p.cout + c]; s2 += sstat[(size_t)w * 2 * p.cout + p.cout + c]; }
+        atomicAdd(p.st_scratch + 2 * c, (double)s1);
+        atomicAdd(p.st_scratch + 2 * c + 1, (double)s2);
+      }
+      __threadfence();
+      volatile int& last_cta = *reinterpret_cast<volatile int*>(tmem_base_sh + 1);   // (static smem would exceed the 227 KB opt-in)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(p.st_scratch + 2 * 256);
+        last_cta = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+        if (last_cta) *ticket = 0u;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (last_cta) {
+        __threadfence();
+        for (int c = et; c < p.cout_valid; c += 128) {
+          const double sum = __ldcg(p.st_scratch + 2 * c), sq = __ldcg(p.st_scratch + 2 * c + 1);
+          p.st_scratch[2 * c] = 0.0; p.st_scratch[2 * c + 1] = 0.0;
+          const double mean = sum / (double)p.st_count;
+          double var = sq / (double)p.st_count - mean * mean;
+          if (var < 0.0) var = 0.0;
+          const float rs = (float)(1.0 / sqrt(var + (double)p.st_eps));
+          const float g = p.st_gamma ? p.st_gamma[c] : 1.f, be = p.st_beta ? p.st_beta[c] : 0.f;
+          const float av = g * rs;
+          p.st_a[c] = av; p.st_b[c] = be - (float)mean * av; p.st_rstd[c] = rs; p.st_mean[c] = (float)mean;
+          if (p.st_rm) {
+            const double unb = p.st_count > 1 ? var * (double)p.st_count / (double)(p.st_count - 1) : var;
+            p.st_rm[c] = (1.f - p.st_mom) * p.st_rm[c] + p.st_mom * (float)mean;
+            p.st_rv[c] = (1.f - p.st_mom) * p.st_rv[c] + p.st_mom * (float)unb;
+          }
+        }
+      }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------ weight packing
+// fp32 (Cout, Cin, kh, kw) -> per (group, tap, k-block) blobs [hi: cout x 16 ch][lo: cout x 16 ch], each in the
+// UMMA SWIZZLE_NONE K-major core-matrix order: blob[n/8][kk/8][n%8][kk%8] (LBO = 128 B, SBO = 256 B); tap = ky*kw + kx.
+__global__ void pack_rect_kernel(const float* __restrict__ w, int cin_w, int cout_w, int kh, int kw,
+                                 int cin_pad, int cout_pad, int nsplit, uint8_t* __restrict__ out)
+{
+  const int taps = kh * kw;
+  const int stage_bytes = cout_pad * 32 * (nsplit == 3 ? 2 : 1);
+  const long long total = (long long)cin_pad * cout_pad * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cin_pad);
+    const int nn = (int)((i / cin_pad) % cout_pad);
+    const int tap = (int)(i / ((long long)cin_pad * cout_pad));
+    const int ky = tap / kw, kx = tap - ky * kw;
+    float v = 0.f;
+    if (c < cin_w && nn < cout_w) v = w[(((size_t)nn * cin_w + c) * kh + ky) * kw + kx];
+    const int g = c / kGroupCh, cg = c - g * kGroupCh;
+    const int gch = min(kGroupCh, cin_pad - g * kGroupCh);
+    const int kbg = gch / 16;
+    const int stage = g * taps * (kGroupCh / 16) + tap * kbg + cg / 16;
+    const int kk = cg & 15;
+    const size_t off = (size_t)stage * stage_bytes + (size_t)(nn >> 3) * 256 + (size_t)(kk >> 3) * 128 + (size_t)(nn & 7) * 16 + (size_t)(kk & 7) * 2;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    *reinterpret_cast<__nv_bfloat16*>(out + off) = h;
+    if (nsplit == 3) *reinterpret_cast<__nv_bfloat16*>(out + off + (size_t)cout_pad * 32) = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// (Cout, Cin, k, k) -> the column-conv weight (k*Cout, Cin, k, 1): row kx*Cout + co holds W[co, :, :, kx]
+__global__ void kx_rearrange_kernel(const float* __restrict__ w, int cin, int cout, int k, float* __restrict__ out)
+{
+  const long long total = (long long)cout * cin * k * k;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kx = (int)(i % k);
+    const int ky = (int)((i / k) % k);
+    const int c = (int)((i / ((long long)k * k)) % cin);
+    const int co = (int)(i / ((long long)k * k * cin));
+    out[(((size_t)(kx * cout + co)) * cin + c) * k + ky] = w[i];
+  }
+}
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+extern "C" size_t cvd_convr_packed_bytes(int cin, int cout, int kh, int kw, int precision)
+{
+  const int cin_pad = round_up(cin, 16), cout_pad = round_up(cout, 16);
+  return (size_t)cin_pad * cout_pad * kh * kw * 2 * (precision == 3 ? 2 : 1);
+}
+
+extern "C" int cvd_convr_pack_weights(const float* w_oihw, int cin, int cout, int kh, int kw, int precision, void* packed, void* stream)
+{
+  CVD_CHECK_ARG(w_oihw && packed, "cvd_convr_pack_weights: null pointer");
+  CVD_CHECK_ARG(precision == 1 || precision == 3, "cvd_convr_pack_weights: precision must be 1 or 3");
+  CVD_CHECK_ARG(cout <= 256, "cvd_convr_pack_weights: cout=%d > 256", cout);
+  const int cin_pad = round_up(cin, 16), cout_pad = round_up(cout, 16);
+  const long long total = (long long)cin_pad * cout_pad * kh * kw;
+  long long blocks = (total + 255) / 256; if (blocks > 4096) blocks = 4096;
+  pack_rect_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, cin, cout, kh, kw, cin_pad, cout_pad, precision, (uint8_t*)packed);
+  CVD_LAUNCH_OK("pack_rect_kernel");
+  return 0;
+}
+
+extern "C" int cvd_kx_rearrange_weights(const float* w_oihw, int cin, int cout, int k, float* w_col, void* stream)
+{
+  CVD_CHECK_ARG(w_oihw && w_col && cin > 0 && cout > 0 && k > 0, "cvd_kx_rearrange_weights: bad arguments");
+  const long long total = (long long)cout * cin * k * k;
+  long long blocks = (total + 255) / 256; if (blocks > 4096) blocks = 4096;
+  kx_rearrange_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, cin, cout, k, w_col);
+  CVD_LAUNCH_OK("kx_rearrange_kernel");
+  return 0;
+}
+
+extern "C" int cvd_convr_fwd(const cvd_src_t* src, const void* packed_w, const float* bias, const cvd_dst_t* dst,
+                             int N, int H, int W, int Wout, int cin, int cout, int kh, int kw, int pad_y, int pad_x,
+                             int precision, int flags, void* stream)
+{
+  CVD_CHECK_ARG(src && dst && packed_w && src->x && dst->y, "cvd_convr_fwd: null pointer");
+  CVD_CHECK_ARG(precision == 1 || precision == 3, "cvd_convr_fwd: precision must be 1 (bf16) or 3 (bf16x3)");
+  CVD_CHECK_ARG(kh >= 1 && kh <= 11 && kw >= 1 && kw <= 11 && Wout >= W && pad_y >= 0 && pad_x >= 0, "cvd_convr_fwd: filter %dx%d unsupported", kh, kw);
+  CVD_CHECK_ARG(N > 0 && H > 0 && W > 0, "cvd_convr_fwd: bad shape");
+  CVD_CHECK_ARG(src->mode == CVD_XF_AFFINE || (src->mode == CVD_XF_BNBWD && src->dy && src->bw && src->a && src->b),
+                "cvd_convr_fwd: bad source transform");
+  CVD_CHECK_ARG((src->c_total & 3) == 0 && (src->c_off & 3) == 0 && (src->n0 & 7) == 0 && (src->gap & 3) == 0,
+                "cvd_convr_fwd: source view must be 4-channel aligned");
+  CVD_CHECK_ARG((dst->c_total & 3) == 0 || dst->c_total == 1, "cvd_convr_fwd: destination channel stride must be a multiple of 4 (or 1)");
+  ConvArgs p{};
+  fillns::SrcView& v = p.src;
+  v.x = src->x; v.dy = src->dy; v.a = src->a; v.b = src->b; v.bw = reinterpret_cast<const float4*>(src->bw);
+  v.ct = src->c_total; v.c0 = src->c_off; v.n0 = src->n0 > 0 ? src->n0 : (1 << 30); v.gap = src->gap;
+  v.dy_ct = src->dy_ctotal; v.dy_c0 = src->dy_coff; v.dy_n0 = src->dy_n0 > 0 ? src->dy_n0 : (1 << 30); v.dy_gap = src->dy_gap;
+  v.relu = src->relu; v.mode = src->mode;
+  v.cvalid = round_up(cin, 4);
+  p.wp = (const uint8_t*)packed_w; p.bias = bias;
+  p.y = dst->y; p.y_ct = dst->c_total; p.y_c0 = dst->c_off; p.y_n0 = dst->n0 > 0 ? dst->n0 : (1 << 30); p.y_gap = dst->gap;
+  p.cout_valid = cout;
+  p.N = N; p.H = H; p.W = W; p.Wout = Wout; p.kh = kh; p.kw = kw; p.pad_y = pad_y; p.pad_x = pad_x;
+  p.cin = round_up(cin, 16); p.cout = round_up(cout, 16);
+  CVD_CHECK_ARG(p.cout <= 256, "cvd_convr_fwd: cout=%d > 256", cout);
+  p.flags = flags; p.nsplit = precision;
+  const int ng64 = (p.cin + kGroupCh - 1) / kGroupCh;
+  p.kb_bytes = p.cout * 32 * (precision == 3 ? 2 : 1);
+
+  // Choose the CTA tile (M-tiles of 8x16 px), the channels per staging slot (64, or 32 = "gsplit 2") and the
+  // number of slots.  Two TMEM accumulator buffers: 2 * MT * cout <= 512 columns.  Preference: two slots
+  // (staging overlaps the MMAs) with the largest tile that fits; else one slot.
+  const int smem_budget = 212 * 1024;
+  const int cand[6][2] = {{4, 2}, {4, 1}, {2, 2}, {2, 1}, {1, 2}, {1, 1}};   // (mtx, mty), largest first
+  bool found = false;
+  // Grid fill: a persistent CTA owns whole tiles, so on small feature maps the largest tile leaves most SMs idle
+  // (28x48x8 frames in 32x32-pixel tiles = 16 CTAs).  Prefer the largest tile that still yields >= one tile per SM,
+  // then relax the requirement step by step (CVD_TILE_FILL=0 restores "largest tile that fits").
+  static const bool fill_grid = !(getenv("CVD_TILE_FILL") && getenv("CVD_TILE_FILL")[0] == '0');
+  for (int min_tiles = fill_grid ? cvd_num_sms() : 0; !found; min_tiles = min_tiles > 8 ? min_tiles / 2 : 0) {
+  for (int want_slots = 2; want_slots >= 1 && !found; --want_slots) {
+    for (int ci = 0; ci < 6 && !found; ++ci) {
+      const int mtx = cand[ci][0], mty = cand[ci][1];
+      if (2 * mtx * mty * p.cout > 512) continue;
+      if ((long long)N * ((Wout + 8 * mtx - 1) / (8 * mtx)) * ((H + 16 * mty - 1) / (16 * mty)) < min_tiles) continue;
+      if (8 * mtx > round_up(Wout, 8) && mtx > 1) continue;
+      if (16 * mty > round_up(H, 16) && mty > 1) continue;
+      const int HP = 16 * mty + kh - 1, WP = 8 * mtx + kw - 1;
+      for (int gsplit = 1; gsplit <= 2 && !found; ++gsplit) {
+        if (gsplit == 2 && (p.cin % kGroupCh != 0)) continue;
+        const int gchunks = gsplit == 2 ? 4 : (ng64 == 1 ? p.cin : kGroupCh) / 8;
+        const int items = gsplit == 2 ? 2 * ng64 : ng64;
+        int plane = HP * WP * 16;
+        // producer store bank spreading: plane stride = 16*q (mod 128) with q = pixels per quarter-warp
+        const int q = gchunks >= 8 ? 1 : 8 / gchunks;
+        plane = (plane + 127) / 128 * 128 + 16 * q;
+        const int slot = plane * gchunks * (precision == 3 ? 2 : 1);
+        // k-blocks per weight stage: divides every item's k-block count, stage <= 16 KB
+        const int last_kb = gsplit == 2 ? 2 : ((p.cin - (ng64 - 1) * kGroupCh) >> 4);
+        const int full_kb = gsplit == 2 ? 2 : ((ng64 > 1 ? kGroupCh : p.cin) >> 4);
+        int kbs = 4;
+        while (kbs > 1 && (last_kb % kbs != 0 || full_kb % kbs != 0 || kbs * p.kb_bytes > 16384)) kbs >>= 1;
+        const int stage_bytes = kbs * p.kb_bytes;
+        const int stages_per_tile = kh * kw * (p.cin >> 4) / kbs;
+        for (int nst = kMaxStages; nst >= 2 && !found; --nst) {
+          if ((size_t)want_slots * slot + (size_t)nst * stage_bytes + 1024 + fillns::param_bytes(p.cin) + 32 * p.cout > (size_t)smem_budget) continue;
+          p.mtx = mtx; p.mty = mty; p.nslots = want_slots; p.gsplit = gsplit; p.gchunks = gchunks; p.ngroups = items;
+          p.HP = HP; p.WP = WP; p.plane_bytes = plane; p.slot_bytes = slot;
+          p.kbs = kbs; p.stage_bytes = stage_bytes;
+          p.nstages = nst > stages_per_tile && stages_per_tile >= 1 ? (stages_per_tile < 2 ? 2 : stages_per_tile) : nst;
+          if (p.nstages > kMaxStages) p.nstages = kMaxStages;
+          found = true;
+        }
+      }
+    }
+  }
+    if (min_tiles == 0) break;
+  }
+  CVD_CHECK_ARG(found, "cvd_convr_fwd: no tile fits shared memory (cin=%d cout=%d k=%dx%d)", cin, cout, kh, kw);
+  p.tiles_x = (Wout + 8 * p.mtx - 1) / (8 * p.mtx);
+  p.tiles_y = (H + 16 * p.mty - 1) / (16 * p.mty);
+  p.ntiles = N * p.tiles_x * p.tiles_y;
+  int cols = 2 * p.mtx * p.mty * p.cout, pw = 32;
+  while (pw < cols) pw <<= 1;
+  p.tmem_cols = pw;
+  CVD_CHECK_ARG(p.plane_bytes < (1 << 18) && p.WP * 16 < (1 << 18), "cvd_convr_fwd: descriptor offset overflow");
+
+  const size_t smem = (size_t)p.nslots * p.slot_bytes + (size_t)p.nstages * p.stage_bytes + 1024 + fillns::param_bytes(p.cin) + 32 * p.cout;
+  const long long grid = p.ntiles < cvd_num_sms() ? p.ntiles : cvd_num_sms();   // persistent: one CTA per SM
+  const int MT = p.mtx * p.mty;
+  cudaError_t e = cudaSuccess;
+#define CVD_CONV_LAUNCH(MTV, NS)                                                                             \
+  do {                                                                                                       \
+    static bool cfg = false;                                                                                 \
+    if (!cfg) {                                                                                              \
+      e = cudaFuncSetAttribute(convr_kernel<MTV, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)); \
+      cfg = true;                                                                                            \
+    }                                                                                                        \
+    if (e == cudaSuccess) convr_kernel<MTV, NS><<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(p); \
+  } while (0)
+#define CVD_CONV_MT(NS)                                                                                      \
+  do {                                                                                                       \
+    if (MT == 8) CVD_CONV_LAUNCH(8, NS); else if (MT == 4) CVD_CONV_LAUNCH(4, NS);                           \
+    else if (MT == 2) CVD_CONV_LAUNCH(2, NS); else CVD_CONV_LAUNCH(1, NS);                                   \
+  } while (0)
+  if (precision == 3) CVD_CONV_MT(3); else CVD_CONV_MT(1);
+  if (e != cudaSuccess) return cvd_fail("cvd_convr_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  CVD_LAUNCH_OK("convr_kernel");
+  return 0;
+}
+

@@ -176,6 +176,9 @@ class McEngine:
         import os
         self.multi_stream = os.environ.get("CVD_MULTI_STREAM", "1") == "1"
         self.fuse_bn = os.environ.get("CVD_FUSE_BN", "1") == "1"     # BN batch statistics in the conv epilogue
+        # EXPERIMENTAL (not validated on hardware yet): forward convs with k*Cout <= 256 through the
+        # kx-fused column conv + shifted sum instead of k*k taps of N = Cout
+        self.kxfwd = os.environ.get("CVD_KXFWD", "0") == "1"
         self.side_streams = []
         self.pmap, self.grad_flat = params.pmap, params.grad_flat
         self._p, self._g, self._rb = params._p, params._g, params._rb
@@ -231,6 +234,17 @@ class McEngine:
         self.pack_fwd.append((Wt, pk, False))
         self.raw_outputs[wkey[:-7]] = (dst.buf, dst.off, cout)       # conv prefix -> where its raw output lives
         s, d = x.src(), ops.make_dst(dst.view())
+        if self.kxfwd and bn is not None and k >= 3 and flags == 0 and k * cout <= 256 and cout % 16 == 0 and dst.gap == 0:
+            t, rm, rv, gamma, beta, si = bn
+            bufs = ops.kxfwd_buffers(cin, cout, k, N, h, w, prec, self.dev)
+            dv, scratch, npix = dst.view(), self.conv_scratch[si], N * h * w
+
+            def run_kx():
+                ops.conv_kxfwd(s, Wt, bias, dv, N, h, w, cin, cout, k, prec, bufs)
+                if self.train_mode:
+                    ops.bn_stats(dst.buf, dst.off, cout, npix, scratch, t.a, t.b, t.rstd, t.mean, gamma, beta, rm, rv)
+            self.fwd.append(run_kx)
+            return pk
         bns = None
         if bn is not None:     # (tensor record, running_mean, running_var, gamma, beta, scratch index): fused batch statistics
             t, rm, rv, gamma, beta, si = bn

@@ -328,3 +328,28 @@ def recip_relu(raw4, depth):
 def recip_relu_bwd(ddepth, depth, raw4, draw4):
     _lib.check(_lib.lib().cvd_recip_relu_bwd(_lib.ptr(ddepth), _lib.ptr(depth), _lib.ptr(raw4), _lib.ptr(draw4),
                                              C.c_longlong(depth.numel()), _lib.stream()), "cvd_recip_relu_bwd")
+
+
+# ---------------------------------------------------------------- experimental kx-fused forward conv (CVD_KXFWD=1)
+def kxfwd_buffers(cin, cout, k, N, H, W, precision, device):
+    """(rearranged weight (k*cout, cin, k, 1), packed blob, column-conv output D (N, H, W+k-1, k*cout))."""
+    kc = k * cout
+    wcol = torch.empty(kc, cin, k, 1, device=device)
+    pk = torch.empty(int(_lib.lib().cvd_convr_packed_bytes(cin, kc, k, 1, precision)), dtype=torch.uint8, device=device)
+    D = torch.empty(N, H, W + k - 1, kc, device=device)
+    return wcol, pk, D
+
+
+def conv_kxfwd(src, w_oihw, bias, dst_view, N, H, W, cin, cout, k, precision, bufs):
+    """dst_view (View) = conv_kxk(src) + bias through the column conv (N = k*cout GEMM columns) + shifted sum."""
+    wcol, pk, D = bufs
+    L, st = _lib.lib(), _lib.stream()
+    kc, pad = k * cout, (k - 1) // 2
+    _lib.check(L.cvd_kx_rearrange_weights(_lib.ptr(w_oihw), cin, cout, k, _lib.ptr(wcol), st), "cvd_kx_rearrange_weights")
+    _lib.check(L.cvd_convr_pack_weights(_lib.ptr(wcol), cin, kc, k, 1, precision, _lib.ptr(pk), st), "cvd_convr_pack_weights")
+    d = make_dst(View(D, 0))
+    _lib.check(L.cvd_convr_fwd(C.byref(src), _lib.ptr(pk), None, C.byref(d), N, H, W, W + k - 1, cin, kc, k, 1, pad, pad,
+                               precision, 0, st), "cvd_convr_fwd")
+    assert dst_view.gap == 0 or dst_view.n0 >= cout
+    _lib.check(L.cvd_shift_sum(_lib.ptr(D), kc, _lib.ptr(bias), _lib.ptr(dst_view.t), dst_view.c_total, dst_view.off,
+                               N, H, W, k, cout, st), "cvd_shift_sum")

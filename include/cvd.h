@@ -327,6 +327,24 @@ int cvd_up2_bilinear_bwd(const float* dout, int N, int h, int w, int C, int alig
 int cvd_recip_relu_fwd(const float* raw4, float* depth, long long n, void* stream);
 int cvd_recip_relu_bwd(const float* ddepth, const float* depth, const float* raw4, float* draw4, long long n, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * EXPERIMENTAL (off unless CVD_KXFWD=1): kx-fused forward convolution for layers with few output
+ * channels.  A k x k conv with Cout outputs = a k x 1 column conv with k*Cout GEMM columns
+ *   D[n, y, x', kx*Cout + co] = sum_{ky, ci} X[n, y + ky - pad, x' - pad, ci] * W[co, ci, ky, kx],  x' in [0, W + k - 1)
+ * (cvd_convr_fwd with kh = k, kw = 1, pad_y = pad_x = pad, Wout = W + k - 1 on weights rearranged by
+ * cvd_kx_rearrange_weights and packed by cvd_convr_pack_weights) followed by
+ *   out[n, y, x, co] = bias[co] + sum_kx D[n, y, x + kx, kx*Cout + co]                    (cvd_shift_sum).
+ * cvd_convr_fwd is cvd_conv_fwd generalised to kh x kw filters, separate paddings and an output wider than the input.
+ * ------------------------------------------------------------------------------------------------ */
+size_t cvd_convr_packed_bytes(int cin, int cout, int kh, int kw, int precision);
+int cvd_convr_pack_weights(const float* w_oihw, int cin, int cout, int kh, int kw, int precision, void* packed, void* stream);
+int cvd_kx_rearrange_weights(const float* w_oihw, int cin, int cout, int k, float* w_col, void* stream);
+int cvd_convr_fwd(const cvd_src_t* src, const void* packed_w, const float* bias, const cvd_dst_t* dst,
+                  int N, int H, int W, int Wout, int cin, int cout, int kh, int kw, int pad_y, int pad_x,
+                  int precision, int flags, void* stream);
+int cvd_shift_sum(const float* D, int d_ctotal, const float* bias, float* out, int o_ctotal, int o_coff,
+                  int N, int H, int W, int k, int cout, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,7 @@ class _Recorder:
         self.real, self.calls, self.args = real, collections.Counter(), collections.defaultdict(list)
 
     def __getattr__(self, name):
-        if name in ("cvd_bn_scratch_bytes", "cvd_conv_packed_bytes"):
+        if name in ("cvd_bn_scratch_bytes", "cvd_conv_packed_bytes", "cvd_convr_packed_bytes"):
             return getattr(self.real, name)
 
         def f(*a):
@@ -97,3 +97,19 @@ def test_midas_plan(fake_lib):
     assert fake_lib.calls["cvd_conv_wgrad"] == len(dense) and fake_lib.calls["cvd_conv_wgrad_grouped"] == chunks
     assert fake_lib.calls["cvd_bn_bwd_reduce"] == 104                                              # 104 BatchNorms
     _check_weight_coverage(P, midas_arch, fake_lib, chunk_rows=CHUNK)
+
+
+def test_kx_fused_forward_call_sequence(fake_lib):
+    """Experimental path: rearrange -> pack -> column conv (kh = k, kw = 1, Wout = W + k - 1, N = k*Cout) -> shifted sum."""
+    from consistent_depth_b200 import ops
+    N, H, W, cin, cout, k = 2, 8, 12, 64, 16, 11
+    x, y = torch.zeros(N, H, W, cin), torch.zeros(N, H, W, 48)
+    w, bias = torch.zeros(cout, cin, k, k), torch.zeros(cout)
+    bufs = ops.kxfwd_buffers(cin, cout, k, N, H, W, 3, "cpu")
+    assert bufs[0].shape == (k * cout, cin, k, 1) and bufs[2].shape == (N, H, W + k - 1, k * cout)
+    ops.conv_kxfwd(ops.make_src(ops.View(x, 0)), w, bias, ops.View(y, 16), N, H, W, cin, cout, k, 3, bufs)
+    assert [n for n in fake_lib.calls] == ["cvd_kx_rearrange_weights", "cvd_convr_pack_weights", "cvd_convr_fwd", "cvd_shift_sum"]
+    a = fake_lib.args["cvd_convr_fwd"][0]
+    assert a[4:14] == (N, H, W, W + k - 1, cin, k * cout, k, 1, 5, 5)
+    s = fake_lib.args["cvd_shift_sum"][0]
+    assert s[1] == k * cout and s[4:] [:7] == (48, 16, N, H, W, k, cout)
