@@ -345,6 +345,15 @@ int cvd_convr_fwd(const cvd_src_t* src, const void* packed_w, const float* bias,
 int cvd_shift_sum(const float* D, int d_ctotal, const float* bias, float* out, int o_ctotal, int o_coff,
                   int N, int H, int W, int k, int cout, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * SURVEY §8(f) rank 3 (not yet validated on hardware): the flow + photometric consistency masks of
+ * utils/consistency.py:53-67 (flow.py:199-228) for B frame pairs, both directions, in one launch.
+ * flows (B, 2 directions, 2, H, W): [b,0] = flow frame0 -> frame1, [b,1] = flow frame1 -> frame0 (pixels);
+ * colors (B, 2 frames, 3, H, W); masks (B, 2 directions, H, W) float {0, 1}.
+ * ------------------------------------------------------------------------------------------------ */
+int cvd_flow_consistency_masks(const float* flows, const float* colors, float* masks, int B, int H, int W,
+                               float flow_thresh, float color_thresh, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,7 @@ fixtures hold only what the real reference modules produced for them:
   midas_small.npz   : monodepth/midas_v2/midas_net.py MidasNet (trunk = torchvision resnext101_32x8d in place of the
                       unreachable torch.hub WSL model, same layer graph) driven as monodepth/midas_v2_model.py:52-69
                       does, train mode, + grads of the consistency loss (lambda_view_baseline = 1e-4), BN running stats
+  flowmask.npz      : utils/consistency.py consistent_flow_masks (+ its sample()) on two synthetic frame pairs
   finetune_steps.npz: depth_fine_tuning.py:261-283 inner loop (model -> zero_grad -> JointLoss ->
                       backward -> step), 3 steps on one pair
 """
@@ -29,7 +30,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
-from oracle import ref_import, synth, hourglass_oracle as ho, monodepth2_oracle as m2, midas_oracle as mo  # noqa: E402
+from oracle import ref_import, synth, hourglass_oracle as ho, monodepth2_oracle as m2, midas_oracle as mo, flowmask_oracle as fo  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
@@ -220,6 +221,23 @@ def gen_midas():
     print("midas loss", out["loss"], "ngrads", len(names), "disparity range", float(output.min()), float(output.max()))
 
 
+FLOWMASK_CASES = {"a": (71, 24, 40, 1.0, 0.5), "b": (72, 17, 31, 1.5, 0.4)}     # seed, H, W, flow_thresh, color_thresh
+
+
+def gen_flowmask():
+    from utils import consistency
+    out = {}
+    for name, (seed, H, W, ft, ct) in FLOWMASK_CASES.items():
+        flows, colors = fo.synthetic_pair(seed, H, W)
+        masks = consistency.consistent_flow_masks(flows, colors, ft, ct)
+        out[f"{name}_mask0"], out[f"{name}_mask1"] = masks[0], masks[1]
+        X, Y = np.meshgrid(np.arange(W), np.arange(H))
+        uv = np.stack((flows[0][..., 0] + X, flows[0][..., 1] + Y), -1)
+        out[f"{name}_sample"] = consistency.sample(colors[1], uv)
+        print("flowmask", name, "kept", float(masks[0].mean()), float(masks[1].mean()))
+    np.savez_compressed(os.path.join(OUT, "flowmask.npz"), **out)
+
+
 def gen_adam():
     import optimizer
     p0 = synth.normal(31, 1, (1003,), 0.1)
@@ -267,14 +285,14 @@ def gen_finetune():
 
 def main():
     ap = argparse.ArgumentParser(description=__doc__)
-    ap.add_argument("--only", default=None, help="generate one fixture family: consistency|adam|hourglass|finetune|monodepth2|midas")
+    ap.add_argument("--only", default=None, help="generate one fixture family: consistency|adam|hourglass|finetune|monodepth2|midas|flowmask")
     only = ap.parse_args().only
     ref_import.setup()
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     os.makedirs(OUT, exist_ok=True)
     gens = {"consistency": gen_consistency, "adam": gen_adam, "hourglass": gen_hourglass, "finetune": gen_finetune,
-            "monodepth2": gen_monodepth2, "midas": gen_midas}
+            "monodepth2": gen_monodepth2, "midas": gen_midas, "flowmask": gen_flowmask}
     for name, fn in gens.items():
         if only is None or only == name:
             fn()

@@ -1,0 +1,24 @@
+"""GPU, OPT-IN (CVD_TEST_FLOWMASK=1): cvd_flow_consistency_masks against the oracle and the golden masks the reference's
+utils/consistency.py produced.  Opt-in because the kernel was written after the round's GPU budget was spent."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import flowmask_oracle as fo
+from oracle.make_golden import FLOWMASK_CASES
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("CVD_TEST_FLOWMASK") != "1", reason="unvalidated kernel: set CVD_TEST_FLOWMASK=1")]
+
+
+@pytest.mark.parametrize("name", list(FLOWMASK_CASES))
+def test_flow_consistency_masks_match_reference(name):
+    from consistent_depth_b200.utils.consistency import consistent_flow_masks
+    seed, H, W, ft, ct = FLOWMASK_CASES[name]
+    flows, colors = fo.synthetic_pair(seed, H, W)
+    masks = consistent_flow_masks(flows, colors, ft, ct)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "flowmask.npz"))
+    want = fo.consistent_flow_masks(flows, colors, ft, ct)
+    for d in range(2):
+        assert masks[d].shape == (H, W) and masks[d].dtype == bool
+        assert (masks[d] != want[d]).mean() <= 2e-3 and (masks[d] != g[f"{name}_mask{d}"]).mean() <= 2e-3
