@@ -12,50 +12,19 @@
 #include "../../include/cvd.h"
 #include "cvd_common.cuh"
 
+// The per-pixel arithmetic lives in flow_mask_core.h as a __host__ __device__ function so that the CPU test suite can
+// compile it with gcc and check it against the oracle without a GPU (tests/test_flowmask_core_cpu.py).
+#include "flow_mask_core.h"
+
 namespace {
 
 // planar tensors: flows (B, 2 dirs, 2, H, W), colors (B, 2 frames, 3, H, W), masks (B, 2 dirs, H, W) float {0,1}
 __global__ void flow_mask_kernel(const float* __restrict__ flows, const float* __restrict__ colors, float* __restrict__ masks,
                                  int B, int H, int W, float ft2, float ct2)
 {
-  const long long hw = (long long)H * W;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)B * 2 * hw) return;
-  const long long pix = i % hw;
-  const int k = (int)((i / hw) & 1);
-  const long long b = i / (2 * hw);
-  const int x = (int)(pix % W), y = (int)(pix / W);
-  const float* fr = flows + ((size_t)(b * 2 + k) * 2) * hw;           // flow of direction k (ref -> tgt)
-  const float* ft = flows + ((size_t)(b * 2 + (1 - k)) * 2) * hw;     // flow of the opposite direction
-  const float* cr = colors + ((size_t)(b * 2 + k) * 3) * hw;
-  const float* ct = colors + ((size_t)(b * 2 + (1 - k)) * 3) * hw;
-  const float u = fr[pix], v = fr[hw + pix];
-  const float ix = u + (float)x, iy = v + (float)y;
-  bool ok = ix >= 0.f && ix <= (float)(W - 1) && iy >= 0.f && iy <= (float)(H - 1);
-  const float sx = fminf(fmaxf(ix - 0.5f, 0.f), (float)(W - 1)), sy = fminf(fmaxf(iy - 0.5f, 0.f), (float)(H - 1));
-  const int x0 = (int)floorf(sx), y0 = (int)floorf(sy);
-  const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
-  const float tx = sx - (float)x0, ty = sy - (float)y0;
-  const float w00 = (1.f - tx) * (1.f - ty), w01 = tx * (1.f - ty), w10 = (1.f - tx) * ty, w11 = tx * ty;
-  const long long p00 = (long long)y0 * W + x0, p01 = (long long)y0 * W + x1, p10 = (long long)y1 * W + x0, p11 = (long long)y1 * W + x1;
-  float fsse = 0.f;
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    const float* pl = ft + (size_t)c * hw;
-    const float s = -(w00 * __ldg(pl + p00) + w01 * __ldg(pl + p01) + w10 * __ldg(pl + p10) + w11 * __ldg(pl + p11));
-    const float d = fr[(size_t)c * hw + pix] - s;
-    fsse += d * d;
-  }
-  float csse = 0.f;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float* pl = ct + (size_t)c * hw;
-    const float s = w00 * __ldg(pl + p00) + w01 * __ldg(pl + p01) + w10 * __ldg(pl + p10) + w11 * __ldg(pl + p11);
-    const float d = cr[(size_t)c * hw + pix] - s;
-    csse += d * d;
-  }
-  ok = ok && fsse < ft2 && csse < ct2;
-  masks[i] = ok ? 1.f : 0.f;
+  if (i >= (long long)B * 2 * H * W) return;
+  masks[i] = cvd_flow_mask_element(flows, colors, i, H, W, ft2, ct2);
 }
 
 }  // namespace
