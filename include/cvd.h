@@ -354,6 +354,19 @@ int cvd_shift_sum(const float* D, int d_ctotal, const float* bias, float* out, i
 int cvd_flow_consistency_masks(const float* flows, const float* colors, float* masks, int B, int H, int W,
                                float flow_thresh, float color_thresh, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * SURVEY §8(f) rank 4 (not yet run on hardware): the FlowNet2 custom ops, forward only, NCHW fp32.
+ * cvd_correlation_fwd  = correlation_package (correlation_cuda_kernel.cu:51-128; FlowNetC.py:28-31 uses pad = md = 20,
+ *                        K = 1, s1 = 1, s2 = 2): out (B, D*D, Ho, Wo), D = 2 (md / s2) + 1, sizes from cvd_correlation_out_size
+ * cvd_resample2d_fwd   = resample2d_package (resample2d_kernel.cu:17-73, kernel_size 1, bilinear): out = in1 sampled at (x + flow_x, y + flow_y)
+ * cvd_channelnorm_fwd  = channelnorm_package (channelnorm_kernel.cu:16-60, norm_deg 2): out (B,1,H,W) = sqrt(sum_c in^2)
+ * ------------------------------------------------------------------------------------------------ */
+int cvd_correlation_out_size(int H, int W, int pad, int K, int md, int s1, int s2, int* channels, int* Ho, int* Wo);
+int cvd_correlation_fwd(const float* in1, const float* in2, float* out, int B, int C, int H, int W,
+                        int pad, int K, int md, int s1, int s2, void* stream);
+int cvd_resample2d_fwd(const float* in1, const float* flow, float* out, int B, int C, int H, int W, void* stream);
+int cvd_channelnorm_fwd(const float* in, float* out, int B, int C, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,7 @@ class _Recorder:
         self.real, self.calls, self.args = real, collections.Counter(), collections.defaultdict(list)
 
     def __getattr__(self, name):
-        if name in ("cvd_bn_scratch_bytes", "cvd_conv_packed_bytes", "cvd_convr_packed_bytes"):
+        if name in ("cvd_bn_scratch_bytes", "cvd_conv_packed_bytes", "cvd_convr_packed_bytes", "cvd_correlation_out_size"):
             return getattr(self.real, name)
 
         def f(*a):
@@ -113,3 +113,18 @@ def test_kx_fused_forward_call_sequence(fake_lib):
     assert a[4:14] == (N, H, W, W + k - 1, cin, k * cout, k, 1, 5, 5)
     s = fake_lib.args["cvd_shift_sum"][0]
     assert s[1] == k * cout and s[4:] [:7] == (48, 16, N, H, W, k, cout)
+
+
+def test_flownet2_op_modules_plumbing(fake_lib):
+    """Correlation / Resample2d / ChannelNorm mirrors: constructor surface of the reference modules, output shapes
+    (cvd_correlation_out_size is host-only code and runs for real), argument order of the launches."""
+    from consistent_depth_b200.third_party.flownet2.networks import ChannelNorm, Correlation, Resample2d
+    a, b = torch.zeros(2, 16, 12, 17), torch.zeros(2, 16, 12, 17)
+    out = Correlation(pad_size=20, kernel_size=1, max_displacement=20, stride1=1, stride2=2, corr_multiply=1)(a, b)
+    assert out.shape == (2, 441, 12, 17)                                   # FlowNetC.py:28-31 configuration
+    assert fake_lib.args["cvd_correlation_fwd"][0][3:12] == (2, 16, 12, 17, 20, 1, 20, 1, 2)
+    assert Correlation(pad_size=4, kernel_size=3, max_displacement=4, stride1=2, stride2=1)(a, b).shape == (2, 81, 5, 8)
+    assert Resample2d()(a, torch.zeros(2, 2, 12, 17)).shape == a.shape
+    assert ChannelNorm()(a).shape == (2, 1, 12, 17)
+    with pytest.raises(RuntimeError):
+        Resample2d()(a.requires_grad_(True), torch.zeros(2, 2, 12, 17))
