@@ -18,22 +18,26 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, ret):
+PAIRS = [(0, 1), (1, 3), (2, 6), (4, 5)]
+
+
+def _worker(rank, world, port, ret, B):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from consistent_depth_b200.distributed import allreduce_flat, global_focal, shard_slice
-    B, H, W = 4, 16, 24
-    pairs = [(0, 1), (1, 3), (2, 6), (4, 5)]
+    H, W = 16, 24
+    pairs = PAIRS[:B]
     batch = synth.make_pair_batch(5, pairs, H, W)
-    batch["intrinsics"][1, :, :2] *= 1.1            # make the per-pair focal lengths differ: f must be the GLOBAL mean
+    batch["intrinsics"][-1, :, :2] *= 1.1           # make the per-pair focal lengths differ: f must be the GLOBAL mean
     depth = synth.synth_depth_pred(5, B, H, W)
-    sl = shard_slice(B, rank, world)
+    sl = shard_slice(B, rank, world)                # ragged batches: unequal shares, possibly none (FineTuneStep.step_empty)
     f_dir = global_focal(torch.tensor(batch["intrinsics"]))
     # local loss / gradient with the global scalars, via the oracle's closed form evaluated per direction
     loss_l, grad_l = 0.0, np.zeros((B, 2, H, W))
-    l, r, d, g = co.closed_form(depth[sl], batch["extrinsics"][sl], batch["intrinsics"][sl],
-                                [f[sl] for f in batch["flows"]], [m[sl] for m in batch["masks"]], 1.0, 0.0, B_global=B)
-    loss_l += l; grad_l[sl] += g
+    if sl.stop > sl.start:
+        l, r, d, g = co.closed_form(depth[sl], batch["extrinsics"][sl], batch["intrinsics"][sl],
+                                    [f[sl] for f in batch["flows"]], [m[sl] for m in batch["masks"]], 1.0, 0.0, B_global=B)
+        loss_l += l; grad_l[sl] += g
     store = torch.zeros(B * 2 * H * W + 4, dtype=torch.float64)
     store[:-4] = torch.tensor(grad_l).reshape(-1)
     store[-4] = loss_l
@@ -44,15 +48,18 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-def test_two_rank_sharding_matches_single_process():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("B", [4, 3, 1])          # even, ragged (shares 2 + 1), and a rank without any pair (1 + 0)
+def test_two_rank_sharding_matches_single_process(B):
     world, port = 2, _free_port()
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
-    B, H, W = 4, 16, 24
-    pairs = [(0, 1), (1, 3), (2, 6), (4, 5)]
-    batch = synth.make_pair_batch(5, pairs, H, W)
-    batch["intrinsics"][1, :, :2] *= 1.1
+    mp.spawn(_worker, args=(world, port, ret, B), nprocs=world, join=True)
+    H, W = 16, 24
+    batch = synth.make_pair_batch(5, PAIRS[:B], H, W)
+    batch["intrinsics"][-1, :, :2] *= 1.1
     depth = synth.synth_depth_pred(5, B, H, W)
     l, r, d, g = co.closed_form(depth, batch["extrinsics"], batch["intrinsics"], batch["flows"], batch["masks"], 1.0, 0.0)
     store = ret["store"]
