@@ -182,7 +182,7 @@ def main():
     sd = default_init_state(0)
     sd["pred_layer.weight"] = sd["pred_layer.weight"] * 0.1
     sd["pred_layer.bias"] = torch.full((1,), math.log(2.0))
-    H, W, metric = globals()["H"], globals()["W"], METRIC
+    H, W, bs, metric = globals()["H"], globals()["W"], BS, METRIC      # workload shape (overridden by --workload)
     workload = ("mannequin_challenge hourglass fine-tune step, 224x384, 4 frame pairs (8 frames) per GPU, "
                 "hierarchical2 pairs of 50 synthetic frames, Adam lr 4e-4")
     weights = "seeded default-scale init, output head centred on the scene depth (mc.pth unreachable: no network)"
@@ -197,7 +197,7 @@ def main():
     elif args.workload == "midas2":
         from consistent_depth_b200.monodepth.midas_v2_model import MidasV2Model
         H, W, metric = 384, 672, "frame-pairs/sec fine-tune (midas2 384x672 BS1 per GPU)"
-        globals()["BS"] = 1                      # C3: global batch 8 on 8 GPUs = 1 pair per GPU
+        bs = 1                                   # C3: global batch 8 on 8 GPUs = 1 pair per GPU
         model = MidasV2Model(pretrained=False, precision=args.precision)
         workload = ("MiDaS v2 (ResNeXt-101 32x8d + refinement decoder) fine-tune step, 384x672, 1 frame pair (2 frames) per GPU, "
                     "hierarchical2 pairs of 50 synthetic frames, Adam lr 1e-4")
@@ -209,16 +209,16 @@ def main():
     n_pairs = len(video.pairs)
     gperm = torch.Generator().manual_seed(0)
     order = torch.randperm(n_pairs, generator=gperm).tolist()
-    nb = n_pairs // (BS * world)
+    nb = n_pairs // (bs * world)
     f_dir = None
     if world > 1:
         fm = float(video.intr[:, :2].mean())
         f_dir = (fm, fm)
-    step = FineTuneStep(model, BS, H, W, lr=model.learning_rate, world_size=world, process_group=None)
+    step = FineTuneStep(model, bs, H, W, lr=model.learning_rate, world_size=world, process_group=None)
 
     def batch_ids(it):
-        k = (it % nb) * BS * world + rank * BS
-        return [order[(k + j) % n_pairs] for j in range(BS)]
+        k = (it % nb) * bs * world + rank * bs
+        return [order[(k + j) % n_pairs] for j in range(bs)]
 
     dev_batches = [video.batch(batch_ids(it)) for it in range(nb)]
     host_batches = []
@@ -259,7 +259,7 @@ def main():
         ms = float(tmax)
     clocks = sampler.stop() if sampler else {}
     loss_last = float(step.loss)
-    value = BS * world * args.steps / (ms * 1e-3)
+    value = bs * world * args.steps / (ms * 1e-3)
     gpu_launches = step.launches_per_step * args.steps
 
     # ---------------- end to end through host buffers ("e2e"): pinned host batch -> H2D -> step -> D2H loss
@@ -277,7 +277,7 @@ def main():
         tmax = torch.tensor([ms_e2e], device=dev)
         torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
         ms_e2e = float(tmax)
-    e2e = None if args.no_e2e else {"value": BS * world * args.steps / (ms_e2e * 1e-3), "unit": "frame-pairs/s",
+    e2e = None if args.no_e2e else {"value": bs * world * args.steps / (ms_e2e * 1e-3), "unit": "frame-pairs/s",
                                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4}
 
     # ---------------- roofline of the dominant kernel (tcgen05 conv fwd/dgrad), measured live with CUDA events
@@ -298,7 +298,7 @@ def main():
             "dtype": "bf16x3-split tensor-core MMA, fp32 accumulate/storage" if args.precision == 3 else "bf16 MMA, fp32 accumulate/storage",
             "data": "synthetic",
             "config": {"workload": workload,
-                       "global_batch": BS * world, "parallelism": f"dp{world}",
+                       "global_batch": bs * world, "parallelism": f"dp{world}",
                        "l2_policy": "per-step working set (several GB of activations) >> 126 MB L2; no explicit flush",
                        "weights": weights},
             "roofline": roofline, "roofline_loss_kernel": roof_loss, "cpu_baseline": cpu_base, "e2e": e2e,
