@@ -1,4 +1,11 @@
-"""JointLoss mirror (loss/joint_loss.py:15-47): shape-(1,) total + dict of per-pair sub-losses."""
+"""JointLoss — sum of the enabled loss terms, with the call contract of the reference's loss/joint_loss.py:15-47:
+
+    JointLoss(opt, parameters_init=None)(depths (B,2,H,W), metadata, parameters=None)
+        -> (total loss of shape (1,), {name: per-sample losses})
+
+The parameter term (lambda_parameter > 0) needs the initial parameters at construction and the current ones at call
+time; the geometric-consistency term is on when either of its two weights is positive.
+"""
 from typing import List, Optional
 
 import torch
@@ -12,22 +19,23 @@ class JointLoss(torch.nn.Module):
     def __init__(self, opt, parameters_init=None):
         super().__init__()
         self.opt = opt
+        self.parameter_loss = self.consistency_loss = None
         if opt.lambda_parameter > 0:
-            assert parameters_init is not None
+            assert parameters_init is not None, "lambda_parameter > 0 needs the initial parameters"
             self.parameter_loss = ParameterLoss(parameters_init, opt)
-        if opt.lambda_view_baseline > 0 or opt.lambda_reprojection > 0:
+        if max(opt.lambda_view_baseline, opt.lambda_reprojection) > 0:
             self.consistency_loss = ConsistencyLoss(opt)
 
     def __call__(self, depths, metadata, parameters: Optional[List[Parameter]] = None):
-        loss = torch.zeros(1, dtype=torch.float32, device=depths.device)
-        batch_losses = {}
-        if self.opt.lambda_parameter > 0:
-            assert parameters is not None
-            para_loss, para_batch_losses = self.parameter_loss(parameters)
-            loss = loss + para_loss
-            batch_losses.update(para_batch_losses)
-        if self.opt.lambda_view_baseline > 0 or self.opt.lambda_reprojection > 0:
-            consis_loss, consis_batch_losses = self.consistency_loss(depths, metadata)
-            loss = loss + consis_loss
-            batch_losses.update(consis_batch_losses)
-        return loss, batch_losses
+        terms = []
+        if self.parameter_loss is not None:
+            assert parameters is not None, "lambda_parameter > 0 needs the current parameters"
+            terms.append(self.parameter_loss(parameters))
+        if self.consistency_loss is not None:
+            terms.append(self.consistency_loss(depths, metadata))
+        total = torch.zeros(1, dtype=torch.float32, device=depths.device)
+        per_sample = {}
+        for value, parts in terms:
+            total = total + value
+            per_sample.update(parts)
+        return total, per_sample
