@@ -460,7 +460,7 @@ class McEngine:
         """Plan entries are callables (serial, current stream) or ("par", [branch, ...]): independent branches
         forked onto side streams and joined back — inside the CUDA graph they become parallel branches, which
         keeps the SMs busy on the low-resolution hourglass levels whose kernels have fewer CTAs than the GPU has SMs."""
-        main = torch.cuda.current_stream()
+        main = None
         for op in plan:
             if not isinstance(op, tuple):
                 op()
@@ -471,6 +471,8 @@ class McEngine:
                     for f in br:
                         f()
                 continue
+            if main is None:
+                main = torch.cuda.current_stream()
             while len(self.side_streams) < len(branches) - 1:
                 self.side_streams.append(torch.cuda.Stream(device=self.dev))
             for f in branches[0]:

@@ -128,3 +128,48 @@ def test_flownet2_op_modules_plumbing(fake_lib):
     assert ChannelNorm()(a).shape == (2, 1, 12, 17)
     with pytest.raises(RuntimeError):
         Resample2d()(a.requires_grad_(True), torch.zeros(2, 2, 12, 17))
+
+
+def test_mannequin_challenge_plan(fake_lib):
+    """The hourglass engine's plan (the bench workload's network): launch counts of one forward + backward and
+    weight-gradient coverage -- every conv weight of HourglassModel(3) that trains is the destination of exactly one
+    wgrad launch (the four 1x1 convs of an inception block are ONE fused GEMM whose destination is the first of the four
+    adjacent weights in the flat gradient buffer)."""
+    from consistent_depth_b200.monodepth import mc_arch
+    from consistent_depth_b200.monodepth.mc_engine import McEngine, McParams
+    P = McParams("cpu")
+    e = McEngine(P, 2, 32, 48)
+    assert e.forward(torch.rand(2, 3, 32, 48)).shape == (2, 32, 48)
+    n_inc = sum(1 for k in mc_arch.state_dict_shapes() if k.endswith(".convs.0.0.weight"))
+    assert n_inc == 22
+    fwd_convs = fake_lib.calls["cvd_conv_fwd"] + fake_lib.calls["cvd_conv_fwd_bn"]
+    assert fwd_convs == 1 + 4 * n_inc + 1                      # conv1 + (fused 1x1 + three k x k) per inception + pred layer
+    assert fake_lib.calls["cvd_bn_stats"] == 0                 # statistics come from the conv epilogues
+    e.backward(torch.rand(2, 32, 48))
+    assert fake_lib.calls["cvd_conv_wgrad"] == fwd_convs
+    targets = _wgrad_targets(fake_lib)
+    for k, (off, shape) in P.pmap.items():
+        if len(shape) != 4:
+            continue
+        g = P._g(k)
+        if ".convs." in k and k.endswith(".0.weight") and not k.endswith(".convs.0.0.weight"):
+            assert targets[g.data_ptr()] == 0, k               # 1x1 of branches 1..3: inside the fused GEMM of convs.0.0
+        else:
+            assert targets[g.data_ptr()] == 1, k
+
+
+def test_mannequin_challenge_plan_with_experimental_kx_forward(fake_lib, monkeypatch):
+    """CVD_KXFWD=1: exactly the forward convs with k >= 3 and k * Cout <= 256 take the column-conv route,
+    each followed by the shifted sum and a separate BatchNorm statistics pass; everything else is unchanged."""
+    from consistent_depth_b200.monodepth import mc_arch
+    from consistent_depth_b200.monodepth.mc_engine import McEngine, McParams
+    monkeypatch.setenv("CVD_KXFWD", "1")
+    e = McEngine(McParams("cpu"), 2, 32, 48)
+    assert e.kxfwd
+    e.forward(torch.rand(2, 3, 32, 48))
+    eligible = [k for k, s in mc_arch.state_dict_shapes().items()
+                if len(s) == 4 and ".convs." in k and k.endswith(".3.weight") and s[2] >= 3 and s[2] * s[0] <= 256 and s[0] % 16 == 0]
+    assert len(eligible) > 30
+    for name in ("cvd_kx_rearrange_weights", "cvd_convr_pack_weights", "cvd_convr_fwd", "cvd_shift_sum", "cvd_bn_stats"):
+        assert fake_lib.calls[name] == len(eligible), name
+    assert fake_lib.calls["cvd_conv_fwd"] + fake_lib.calls["cvd_conv_fwd_bn"] == 90 - len(eligible)
