@@ -179,6 +179,9 @@ class McEngine:
         # EXPERIMENTAL (not validated on hardware yet): forward convs with k*Cout <= 256 through the
         # kx-fused column conv + shifted sum instead of k*k taps of N = Cout
         self.kxfwd = os.environ.get("CVD_KXFWD", "0") == "1"
+        # EXPERIMENTAL: fork the side streams BEFORE branch 0 is enqueued so that branch 0 overlaps with the others too
+        # (today the side streams wait on the main stream after branch 0's launches); unmeasured, off by default
+        self.fork_first = os.environ.get("CVD_FORK_FIRST", "0") == "1"
         self.side_streams = []
         self.pmap, self.grad_flat = params.pmap, params.grad_flat
         self._p, self._g, self._rb = params._p, params._g, params._rb
@@ -475,14 +478,18 @@ class McEngine:
                 main = torch.cuda.current_stream()
             while len(self.side_streams) < len(branches) - 1:
                 self.side_streams.append(torch.cuda.Stream(device=self.dev))
-            for f in branches[0]:
-                f()
+            if not self.fork_first:
+                for f in branches[0]:
+                    f()
             for i, br in enumerate(branches[1:]):
                 s = self.side_streams[i]
                 s.wait_stream(main)
                 with torch.cuda.stream(s):
                     for f in br:
                         f()
+            if self.fork_first:
+                for f in branches[0]:
+                    f()
             for i in range(len(branches) - 1):
                 main.wait_stream(self.side_streams[i])
 
