@@ -95,14 +95,18 @@ def host_cpus():
     return n
 
 
+REF_PAIRS = [(0, 1), (1, 2), (2, 4), (0, 3)]      # one BS4 mini-batch of the workload (hierarchical2-style offsets)
+
+
 def cpu_reference_steps(steps, warmup, threads, budget_s=150.0):
-    """The reference's CPU PyTorch path (oracle port of HourglassModel + JointLoss + torch.optim.Adam) on ONE pair
-    (2 frames 224x384) per step: a bounded sample of the BS4 workload.  Returns (pairs/s, seconds per step)."""
+    """The reference's CPU PyTorch path (oracle port of HourglassModel + JointLoss + torch.optim.Adam) on one BS4
+    mini-batch (4 frame pairs = 8 frames 224x384) per step -- the bench configuration itself; the SAMPLE is bounded in
+    steps (time budget), not in batch size.  Returns (pairs/s, seconds per step, timed steps)."""
     import numpy as np
     from oracle import synth, hourglass_oracle as ho, consistency_oracle as co
     torch.set_num_threads(threads)
     P, buffers = ho.to_torch(ho.mc_init_state(7), requires_grad=True)
-    batch = synth.make_pair_batch(1234, [(0, 1)], H, W)
+    batch = synth.make_pair_batch(1234, REF_PAIRS, H, W)
     t = lambda a: torch.tensor(a)
     args = (t(batch["extrinsics"]), t(batch["intrinsics"]), [t(f) for f in batch["flows"]], [t(m) for m in batch["masks"]])
     images = t(batch["images"])
@@ -121,7 +125,73 @@ def cpu_reference_steps(steps, warmup, threads, budget_s=150.0):
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
-    return 1.0 / sec, sec
+    return BS / sec, sec, len(times)
+
+
+def gpu_reference_steps(steps, warmup, dev, allow_tf32):
+    """The reference's GPU PyTorch path on the SAME B200 (SURVEY 8(d) "reference timed beside it (i)": the >= 10x
+    denominator): oracle port of HourglassModel + JointLoss + torch.optim.Adam on cuda, BS4 224x384, cuDNN benchmark on
+    (depth_fine_tuning.py:220-221), one step = depth_fine_tuning.py:264-283 (forward, zero_grad, loss, isnan check with its
+    D2H sync, backward, Adam).  allow_tf32: torch's default for cuDNN convolutions (True) or strict fp32 (False)."""
+    from oracle import synth, hourglass_oracle as ho, consistency_oracle as co
+    old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32)
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = bool(allow_tf32)
+    try:
+        P, buffers = ho.to_torch(ho.mc_init_state(7), requires_grad=False)
+        P = {k: v.to(dev).requires_grad_(True) for k, v in P.items()}
+        buffers = {k: v.to(dev) for k, v in buffers.items()}
+        batch = synth.make_pair_batch(1234, REF_PAIRS, H, W)
+        t = lambda a: torch.tensor(a, device=dev)
+        margs = (t(batch["extrinsics"]), t(batch["intrinsics"]), [t(f) for f in batch["flows"]], [t(m) for m in batch["masks"]])
+        images = t(batch["images"])
+        opt = torch.optim.Adam([P[k] for k in ho.trainable_keys()], 4e-4, betas=(0.9, 0.999))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(warmup + steps):
+            if it == warmup:
+                torch.cuda.synchronize(); e0.record()
+            depth = ho.estimate_depth(images, P, buffers)
+            opt.zero_grad()
+            loss, _ = co.consistency_loss(depth, *margs, 1.0, 0.1)
+            if torch.isnan(loss):                     # the reference's per-iteration sync (:278)
+                continue
+            loss.backward()
+            opt.step()
+        e1.record(); torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3 / steps
+        del P, buffers, opt, depth, loss
+        torch.cuda.empty_cache()
+        return BS / sec, sec
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32 = old
+
+
+def gpu_reference(dev, steps=10, warmup=3):
+    out = {"unit": "frame-pairs/s", "kind": "port", "config": "mannequin_challenge 224x384 BS4, cuDNN benchmark on, 1 GPU",
+           "what": "oracle port of the reference's GPU PyTorch path (HourglassModel + JointLoss + torch.optim.Adam on cuda); "
+                   "the reference tree cannot travel to the GPU box", "steps": steps, "warmup": warmup}
+    for name, tf32 in (("tf32", True), ("fp32", False)):
+        v, sec = gpu_reference_steps(steps, warmup, dev, tf32)
+        out[name] = {"value": v, "ms_per_step": sec * 1e3,
+                     "conv_math": "cuDNN TF32 (torch default)" if tf32 else "strict fp32 (allow_tf32 = False)"}
+    return out
+
+
+def run_reference_gpu(args):
+    """`--impl reference-gpu`: the reference's GPU PyTorch path alone (same JSON shape as the other arms)."""
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    g = gpu_reference(dev, steps=max(args.steps, 3), warmup=max(args.warmup, 3))
+    v = g["tf32"]["value"]
+    print(json.dumps({
+        "impl": "reference-gpu", "metric": METRIC, "value": v, "unit": "frame-pairs/s", "n_gpus": 1, "steps": g["steps"],
+        "warmup": g["warmup"], "ms_per_step": g["tf32"]["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 storage, cuDNN TF32 convolutions (torch default)", "data": "synthetic",
+        "config": {"workload": "mannequin_challenge 224x384 BS4 fine-tune step, reference PyTorch ops on cuda", "parallelism": "dp1"},
+        "gpu_reference": g,
+    }), flush=True)
 
 
 def run_reference(args):
@@ -129,13 +199,14 @@ def run_reference(args):
     if rank != 0:
         return
     threads = host_cpus()
-    v, sec = cpu_reference_steps(args.steps, args.warmup, threads, budget_s=240.0)
-    sample = "1 frame pair (2 frames 224x384) per step: fwd + loss + bwd + Adam, CPU PyTorch fp32 oracle port of the reference"
+    v, sec, done = cpu_reference_steps(args.steps, args.warmup, threads, budget_s=240.0)
+    sample = (f"{done} timed steps x one BS4 mini-batch (4 frame pairs = 8 frames 224x384): fwd + loss + bwd + Adam, "
+              "CPU PyTorch fp32 oracle port of the reference (time-bounded)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frame-pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "mannequin_challenge 224x384 BS4 fine-tune step (bounded sample: BS1 per step)", "parallelism": "cpu"},
+        "config": {"workload": "mannequin_challenge 224x384 BS4 fine-tune step", "global_batch": BS, "parallelism": "cpu"},
         "cpu_baseline": {"value": v, "unit": "frame-pairs/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -147,10 +218,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="cvd", choices=["cvd", "reference"])
+    ap.add_argument("--impl", default="cvd", choices=["cvd", "reference", "reference-gpu"])
     ap.add_argument("--precision", type=int, default=3, choices=[1, 3])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference-GPU-PyTorch leg (gpu_reference)")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer pass")
     ap.add_argument("--workload", default="mc", choices=["mc", "monodepth2", "midas2"],
                     help="mc = BASELINE.json configs[1] (the headline); monodepth2 = configs C4's model at 192x640 BS4 per GPU "
@@ -158,6 +230,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "reference-gpu":
+        return run_reference_gpu(args)
     args.warmup = max(args.warmup, 3)
 
     import __graft_entry__ as graft
@@ -288,9 +362,16 @@ def main():
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline:
         threads = host_cpus()
-        v, sec = cpu_reference_steps(3, 1, threads, budget_s=60.0)
+        v, sec, done = cpu_reference_steps(3, 1, threads, budget_s=60.0)
         cpu_base = {"value": v, "unit": "frame-pairs/s", "cores": threads, "kind": "port",
-                    "sample": "3 steps x 1 frame pair (2 frames 224x384) after 1 warm-up: fwd+loss+bwd+Adam, CPU PyTorch fp32 oracle"}
+                    "sample": f"{done} steps x one BS4 mini-batch (8 frames 224x384) after 1 warm-up: fwd+loss+bwd+Adam, CPU PyTorch fp32 oracle"}
+    gpu_ref = None
+    if rank == 0 and world == 1 and args.workload == "mc" and not args.no_gpu_reference:
+        del step, dev_batches
+        torch.cuda.empty_cache()
+        gpu_ref = gpu_reference(dev)
+        gpu_ref["speedup_e2e_vs_tf32"] = (e2e["value"] if e2e else value) / gpu_ref["tf32"]["value"]
+        gpu_ref["speedup_e2e_vs_fp32"] = (e2e["value"] if e2e else value) / gpu_ref["fp32"]["value"]
     if rank == 0:
         print(json.dumps({
             "metric": metric, "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -301,7 +382,7 @@ def main():
                        "global_batch": bs * world, "parallelism": f"dp{world}",
                        "l2_policy": "per-step working set (several GB of activations) >> 126 MB L2; no explicit flush",
                        "weights": weights},
-            "roofline": roofline, "roofline_loss_kernel": roof_loss, "cpu_baseline": cpu_base, "e2e": e2e,
+            "roofline": roofline, "roofline_loss_kernel": roof_loss, "cpu_baseline": cpu_base, "gpu_reference": gpu_ref, "e2e": e2e,
             "gpu_launches": gpu_launches, "clocks": clocks, "final_loss": loss_last, "peaks_source": pk_src,
         }), flush=True)
     if world > 1:

@@ -129,8 +129,10 @@ __device__ __forceinline__ float pixel_term(
 // gradient coefficients.  Runs once per call (B*2 threads), so the main kernel has no serial prologue.
 __global__ void consistency_setup(const float* __restrict__ extr, const float* __restrict__ intr,
                                   const float* __restrict__ msum, float f0, float f1, int f_given,
+                                  const float* __restrict__ f_dev,
                                   float lam_r, float lam_b, int B, int B_global, PairConst* __restrict__ consts)
 {
+  if (f_dev) { f0 = f_dev[0]; f1 = f_dev[1]; f_given = 1; }   // device-resident global focal length (graph-safe)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * B) return;
   const int b = i >> 1, k = i & 1, t = 1 - k;
@@ -252,9 +254,11 @@ consistency_kernel(const float* __restrict__ depth,
 // acc[b][k][{r,d}] -> out_pair[0][b] = lam_r * mean_k(reproj_k), out_pair[1][b] = lam_b * mean_k(f_k disp_k)
 __global__ void consistency_finalize(const double* __restrict__ acc, const float* __restrict__ msum,
                                      const float* __restrict__ intr, float f0, float f1, int f_given,
+                                     const float* __restrict__ f_dev,
                                      float lam_r, float lam_b, int B, int B_global,
                                      float* __restrict__ out_pair, float* __restrict__ out_loss)
 {
+  if (f_dev) { f0 = f_dev[0]; f1 = f_dev[1]; f_given = 1; }
   __shared__ float fsh[2];
   __shared__ double tot[32];
   if (threadIdx.x < 2) {
@@ -346,7 +350,7 @@ extern "C" int cvd_consistency_fwd_bwd(const float* depth,
                                        const float* flow0, const float* flow1,
                                        const float* mask0, const float* mask1,
                                        const float* extr, const float* intr,
-                                       const float* msum, const float* f_dir_host,
+                                       const float* msum, const float* f_dir_host, const float* f_dir_dev,
                                        float lam_r, float lam_b,
                                        int B, int B_global, int H, int W,
                                        void* workspace, float* out_pair, float* out_loss,
@@ -368,7 +372,7 @@ extern "C" int cvd_consistency_fwd_bwd(const float* depth,
   const int fg = f_dir_host != nullptr;
   const float f0 = fg ? f_dir_host[0] : 0.f, f1 = fg ? f_dir_host[1] : 0.f;
   PairConst* consts = reinterpret_cast<PairConst*>(acc + 4 * (size_t)B);
-  consistency_setup<<<(2 * B + 127) / 128, 128, 0, st>>>(extr, intr, msum, f0, f1, fg, lam_r, lam_b, B, B_global, consts);
+  consistency_setup<<<(2 * B + 127) / 128, 128, 0, st>>>(extr, intr, msum, f0, f1, fg, f_dir_dev, lam_r, lam_b, B, B_global, consts);
   CVD_LAUNCH_OK("consistency_setup");
   dim3 grid((unsigned)((HW + LOSS_THREADS * PIX - 1) / (LOSS_THREADS * PIX)), B);
   const bool full = (HW % (LOSS_THREADS * PIX)) == 0;
@@ -381,7 +385,7 @@ extern "C" int cvd_consistency_fwd_bwd(const float* depth,
 #define CVD_LOSS_R(G) do { if (dr) CVD_LOSS_D(G, true); else CVD_LOSS_D(G, false); } while (0)
   if (gr) CVD_LOSS_R(true); else CVD_LOSS_R(false);
   CVD_LAUNCH_OK("consistency_kernel");
-  consistency_finalize<<<1, 128, 0, st>>>(acc, msum, intr, f0, f1, fg, lam_r, lam_b, B, B_global, out_pair, out_loss);
+  consistency_finalize<<<1, 128, 0, st>>>(acc, msum, intr, f0, f1, fg, f_dir_dev, lam_r, lam_b, B, B_global, out_pair, out_loss);
   CVD_LAUNCH_OK("consistency_finalize");
   return 0;
 }

@@ -42,6 +42,39 @@ class DepthFineTuningParams:
         return parser
 
 
+def log_loss_stats(writer, name_prefix, loss_meta, n, log_histogram=False):
+    """max / min / mean of every sub-loss (reference :66-91)."""
+    for sub, value in loss_meta.items():
+        full = name_prefix + "/" + sub
+        writer.add_scalar(full + "/max", value.max(), n)
+        writer.add_scalar(full + "/min", value.min(), n)
+        writer.add_scalar(full + "/mean", value.mean(), n)
+        if log_histogram:
+            writer.add_histogram(full, value, n)
+
+
+def write_summary(writer, mode_name, input_images, depth, masks, n_iter):
+    """Image grids of the inputs, the predicted depth and the masks (reference :94-117)."""
+    import torchvision.utils as vutils
+    B = depth.shape[0]
+    pred = depth.unsqueeze(-3)
+    mask = torch.stack(masks, dim=1)
+
+    def to_vis(x):
+        return x[:8].transpose(0, 1).reshape((-1,) + x.shape[-3:])
+
+    writer.add_image(mode_name + "/image", vutils.make_grid(to_vis(input_images), nrow=B, normalize=True), n_iter)
+    writer.add_image(mode_name + "/pred_full", vutils.make_grid(to_vis(1.0 / pred), nrow=B, normalize=True), n_iter)
+    writer.add_image(mode_name + "/mask", vutils.make_grid(to_vis(mask), nrow=B, normalize=True), n_iter)
+
+
+def log_loss(writer, mode_name, loss, loss_meta, niters):
+    """Main loss scalar + sub-loss statistics (reference :120-126)."""
+    main = mode_name + "/loss"
+    writer.add_scalar(main, loss, niters)
+    log_loss_stats(writer, main, loss_meta, niters)
+
+
 def make_tag(params):
     return (LossParams.make_str(params) + f"_LR{params.learning_rate}" + f"_BS{params.batch_size}"
             + f"_O{params.optimizer.lower()}")
@@ -59,15 +92,29 @@ class DepthFineTuner:
             params.lambda_view_baseline = model_cls.lambda_view_baseline
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.rank = int(os.environ.get("RANK", "0"))
-        if self.world > 1:                    # reference: batch_size *= num_gpus (:155-159)
-            self.params.batch_size *= self.world
-            print(f"Adjusting batch size to {self.params.batch_size}.")
+        # the run directory is tagged with the batch size BEFORE the multi-GPU scaling, as the reference does (:143 vs :155-159)
         self.out_dir = pjoin(self.range_dir, make_tag(params))
         os.makedirs(self.out_dir, exist_ok=True)
         print(f"Fine-tuning directory: '{self.out_dir}'")
         self.checkpoints_dir = pjoin(self.out_dir, "checkpoints")
         os.makedirs(self.checkpoints_dir, exist_ok=True)
+        if self.world > 1:
+            # one process per GPU (torchrun): bind this rank's device BEFORE the model allocates, and join the NCCL group
+            # that FineTuneStep's gradient all-reduce uses (gloo when no GPU is present: the CPU tests)
+            import torch.distributed as dist
+            if torch.cuda.is_available():
+                torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", self.rank)) % torch.cuda.device_count())
+            if not dist.is_initialized():
+                if "MASTER_ADDR" not in os.environ:
+                    raise RuntimeError("WORLD_SIZE > 1 but no rendezvous: launch with torchrun (MASTER_ADDR/MASTER_PORT/RANK) "
+                                       "or call torch.distributed.init_process_group before constructing DepthFineTuner")
+                # NCCL over NVLink; CVD_DIST_BACKEND=gloo lets two ranks share ONE GPU (single-GPU test boxes)
+                dist.init_process_group(os.environ.get("CVD_DIST_BACKEND", "nccl" if torch.cuda.is_available() else "gloo"))
         self.model = model_cls()
+        print(f"Using {self.world} GPUs.")
+        if self.world > 1:                    # reference: batch_size *= num_gpus (:155-159)
+            self.params.batch_size *= self.world
+            print(f"Adjusting batch size to {self.params.batch_size}.")
         self.vis_depth_scale = None
 
     def save_depth(self, dir=None, frames=None):
@@ -108,16 +155,20 @@ class DepthFineTuner:
         images0, _ = dataset[0]
         H, W = images0.shape[-2:]
         steps = {}
+        # parameters_init (reference :223-224): the weights before fine-tuning, for the lambda_parameter regulariser
+        p_init = self.model.P.flat.detach().clone() if getattr(P, "lambda_parameter", 0.0) > 0 else None
 
         def get_step(b, b_global):
             key = (b, b_global)
             if key not in steps:
                 first = next(iter(steps.values())) if steps else None
                 steps[key] = FineTuneStep(self.model, b, H, W, lr=P.learning_rate, lambda_reprojection=P.lambda_reprojection,
-                                          lambda_view_baseline=P.lambda_view_baseline, world_size=self.world, B_global=b_global)
+                                          lambda_view_baseline=P.lambda_view_baseline, world_size=self.world, B_global=b_global,
+                                          lambda_parameter=getattr(P, "lambda_parameter", 0.0), parameters_init=p_init, rank=self.rank)
                 if first is not None:                            # all batch shapes share ONE Adam state
                     s = steps[key]
                     s.exp_avg, s.exp_avg_sq, s.adam_state = first.exp_avg, first.exp_avg_sq, first.adam_state
+                    s.p_init = first.p_init
             return steps[key]
 
         def validate(epoch, niters):
@@ -130,7 +181,27 @@ class DepthFineTuner:
         self.vis_depth_scale = None
         validate(0, 0)
         total_iters = 0
-        pending = None                                          # (epoch, pairs, loss tensor) of the previous iteration
+        # Logging (reference :277-293): the loss scalar, the per-sub-loss statistics (log_loss_stats :66-91) and the image
+        # summary (:94-117) of iteration i are read back while iteration i+1 runs, so the host never stalls the GPU.
+        pending = None
+
+        def flush(p):
+            if p is None:
+                return 0
+            e, pr, l, meta, n_before, nb_, imgs = p
+            lv = float(l)
+            print(f"Epoch = {e}, pairs = {pr}, loss = {lv}")
+            if lv != lv:                                          # :278-280 (the update was skipped on the device)
+                print("Loss is NaN. Skipping.")
+                return 0
+            n_after = n_before + nb_
+            if writer is not None and self.rank == 0:
+                if n_after % P.print_freq == 0:
+                    log_loss(writer, "Train", l, meta, n_after)
+                if imgs is not None:
+                    write_summary(writer, "Train", *imgs, n_after)
+            return nb_
+
         for epoch in range(P.num_epochs):
             t0 = time.perf_counter()
             for images, metadata in train_loader:
@@ -138,10 +209,11 @@ class DepthFineTuner:
                 sl = shard_slice(nb, self.rank, self.world)      # ragged last batch: uneven shares, possibly none
                 bl = sl.stop - sl.start
                 geom = metadata["geometry_consistency"]
+                pairs = geom["indices"][:nb].tolist()
                 if bl == 0:
                     loss = next(iter(steps.values())).step_empty()
-                    pending = (epoch, geom["indices"][:nb].tolist(), loss.clone())
-                    total_iters += nb
+                    total_iters += flush(pending)
+                    pending = (epoch, pairs, loss.clone(), {}, total_iters, nb, None)
                     continue
                 step = get_step(bl, nb)
                 f_dir = None
@@ -150,18 +222,15 @@ class DepthFineTuner:
                 step.load_batch(images[sl], [f[sl] for f in geom["flows"]], [m[sl] for m in geom["masks"]],
                                 metadata["extrinsics"][sl], metadata["intrinsics"][sl], f_dir)
                 loss = step.step()
-                if pending is not None:                          # log the previous step: no stall on this one
-                    e, pr, l = pending
-                    print(f"Epoch = {e}, pairs = {pr}, loss = {float(l)}")
-                    if writer is not None:
-                        writer.add_scalar("Train/loss", float(l), total_iters)
-                pending = (epoch, geom["indices"][:nb].tolist(), loss.clone())
-                total_iters += nb
-            if pending is not None:
-                e, pr, l = pending
-                lv = float(l)
-                print(f"Epoch = {e}, pairs = {pr}, loss = {lv}" + (" (NaN: step skipped on device)" if lv != lv else ""))
-                pending = None
+                n_prev = flush(pending)                          # the previous step, while this one runs
+                total_iters += n_prev
+                meta = step.loss_meta()                          # device clones, no sync
+                imgs = None
+                if writer is not None and self.rank == 0 and (total_iters + nb) % P.display_freq == 0:
+                    imgs = (step.images.clone(), step.depth().clone(), [m.clone() for m in step.masks])
+                pending = (epoch, pairs, loss.clone(), meta, total_iters, nb, imgs)
+            total_iters += flush(pending)
+            pending = None
             print(f"Epoch {epoch} took {time.perf_counter() - t0:.2f}s.")
             if (epoch + 1) % P.val_epoch_freq == 0:
                 validate(epoch + 1, total_iters)

@@ -28,3 +28,12 @@ def to_one_way(pairs):
 def hierarchical2_one_way(num_frames):
     """Sorted one-way pair list (138 pairs for 50 frames, 286 for 100, 584 for 200)."""
     return sorted(to_one_way(sample_hierarchical2(num_frames, True)))
+
+
+def to_in_range(pairs, frame_range=None):
+    """Keep the pairs whose two frames lie in [frame_range[0], frame_range[1]) (utils/frame_sampling.py:149-156);
+    no range given: all pairs (how loaders/video_dataset.py:120 calls it)."""
+    if frame_range is None:
+        return pairs
+    lo, hi = frame_range[0], frame_range[1]
+    return [p for p in pairs if all(lo <= i < hi for i in p)]

@@ -80,6 +80,7 @@ class VideoDataset(data.Dataset):
             names = os.listdir(os.path.dirname(self.flow_fmt))
             self.flow_indices = [[int(s) for s in os.path.splitext(n)[0].split("_")[-2:]]
                                  for n in names if n.endswith(".raw")]
+            self.flow_indices = frame_sampling.to_in_range(self.flow_indices)
         self.flow_indices = sorted(frame_sampling.to_one_way(tuple(p) for p in self.flow_indices))
 
     def __getitem__(self, index):
@@ -92,6 +93,14 @@ class VideoDataset(data.Dataset):
             "intrinsics": torch.stack([self.intrinsics[k] for k in pair], dim=0),
             "geometry_consistency": {"indices": torch.tensor(pair), "flows": flows, "masks": masks},
         }
+        # optional per-frame / global depth scales (video_dataset.py:196-204): an attribute a caller may set on the dataset;
+        # DepthModel.forward multiplies the prediction by metadata["scales"] when present (depth_model.py:24-28)
+        scales = getattr(self, "scales", None)
+        if scales:
+            if isinstance(scales, dict):
+                metadata["scales"] = torch.stack([torch.Tensor([scales[k]]) for k in pair], dim=0)
+            else:
+                metadata["scales"] = torch.Tensor([scales, scales]).reshape(2, 1)
         return images, metadata
 
     def __len__(self):

@@ -55,6 +55,10 @@ def default_init_state(seed=0):
     return sd
 
 
+def _strip_module(sd):
+    return {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+
+
 class MannequinChallengeModel(DepthModel):
     # Requirements and default settings (mannequin_challenge_model.py:17-19)
     align = 16
@@ -72,10 +76,9 @@ class MannequinChallengeModel(DepthModel):
             path = os.path.join("checkpoints", "mc.pth")
             if os.path.isfile(path):
                 state_dict = torch.load(path, map_location="cpu")
-                state_dict = {k[7:] if k.startswith("module.") else k: v for k, v in state_dict.items()}
             else:
                 state_dict = default_init_state(0)
-        self.P.load_state_dict(state_dict)
+        self.P.load_state_dict(_strip_module(state_dict))
         self.engines = {}
         self.training_ = True
         self._anchor = torch.zeros((), device=self.device_, requires_grad=True)
@@ -128,7 +131,12 @@ class MannequinChallengeModel(DepthModel):
         return self.P.state_dict()
 
     def load_state_dict(self, sd, strict=True):
-        self.P.load_state_dict(sd)
+        """Accepts the reference's checkpoint format (keys prefixed `module.`: netG is DataParallel-wrapped,
+        pix2pix_model.py:108) and bare HourglassModel keys alike."""
+        self.P.load_state_dict(_strip_module(sd))
 
     def save(self, file_name):
-        torch.save(self.P.state_dict(), file_name)
+        """checkpoints/%04d.pth in the reference's format: `netG.state_dict()` of the DataParallel-wrapped hourglass
+        (mannequin_challenge_model.py:71-73), i.e. every key carries the `module.` prefix, so the files are
+        interchangeable with the reference in both directions."""
+        torch.save({"module." + k: v for k, v in self.P.state_dict().items()}, file_name)

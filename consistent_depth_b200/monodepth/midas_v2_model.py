@@ -115,7 +115,8 @@ class MidasV2Model(DepthModel):
         return self.P.state_dict()
 
     def load_state_dict(self, sd, strict=True):
-        self.P.load_state_dict(sd)
+        # the reference wraps MidasNet in DataParallel only when it sees several GPUs (midas_v2_model.py:41-43): accept both
+        self.P.load_state_dict({(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()})
 
     def save(self, file_name):
         torch.save(self.P.state_dict(), file_name)

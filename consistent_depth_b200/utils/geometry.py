@@ -55,12 +55,14 @@ def fused_consistency(depth, flows, masks, extrinsics, intrinsics, lambda_reproj
     out_pair = torch.empty((2, B), dtype=torch.float32, device=dev)
     out_loss = torch.empty((1,), dtype=torch.float32, device=dev)
     grad = torch.empty_like(depth) if want_grad else None
-    fptr = None
-    if f_dir is not None:
+    fptr = fdev = None
+    if torch.is_tensor(f_dir):                # device-resident (2,) tensor: read by the kernels at run time
+        fdev = f_dir
+    elif f_dir is not None:
         fptr = (C.c_float * 2)(float(f_dir[0]), float(f_dir[1]))
     _lib.check(L.cvd_consistency_fwd_bwd(
         _lib.ptr(depth), _lib.ptr(f0), _lib.ptr(f1), _lib.ptr(m0), _lib.ptr(m1),
-        _lib.ptr(extrinsics), _lib.ptr(intrinsics), _lib.ptr(msum), fptr,
+        _lib.ptr(extrinsics), _lib.ptr(intrinsics), _lib.ptr(msum), fptr, _lib.ptr(fdev),
         C.c_float(lambda_reprojection), C.c_float(lambda_view_baseline),
         B, B_global or B, H, W, _lib.ptr(ws["acc"]), _lib.ptr(out_pair), _lib.ptr(out_loss),
         _lib.ptr(grad), st), "cvd_consistency_fwd_bwd")

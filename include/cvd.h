@@ -55,6 +55,10 @@ long long   cvd_launch_count(void);
  *   f_dir_host [2] or NULL mean focal length over the GLOBAL batch for
  *                          direction k (consistency_loss.py:178); NULL =>
  *                          computed on device from this call's intr.
+ *   f_dir_dev  [2] or NULL the same two scalars in DEVICE memory (read by the
+ *                          kernels at run time, so a captured CUDA graph stays
+ *                          valid when the global batch's intrinsics change);
+ *                          takes precedence over f_dir_host.
  *   B_global               divisor of the final torch.mean over pairs (:208)
  *   workspace  cvd_consistency_workspace_bytes(B) bytes of device scratch, 16-byte aligned
  *   out_pair   (2,B)  f32  [0]=lambda_r*reprojection[b], [1]=lambda_b*disparity[b]
@@ -73,6 +77,7 @@ int cvd_consistency_fwd_bwd(const float* depth,
                             const float* extr, const float* intr,
                             const float* msum,
                             const float* f_dir_host,
+                            const float* f_dir_dev,
                             float lambda_reprojection, float lambda_view_baseline,
                             int B, int B_global, int H, int W,
                             void* workspace, float* out_pair, float* out_loss,

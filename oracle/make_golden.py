@@ -17,6 +17,8 @@ fixtures hold only what the real reference modules produced for them:
                       unreachable torch.hub WSL model, same layer graph) driven as monodepth/midas_v2_model.py:52-69
                       does, train mode, + grads of the consistency loss (lambda_view_baseline = 1e-4), BN running stats
   flowmask.npz      : utils/consistency.py consistent_flow_masks (+ its sample()) on two synthetic frame pairs
+  parameter_loss.npz: loss/parameter_loss.py ParameterLoss through loss/joint_loss.py JointLoss (lambda_parameter > 0,
+                      consistency terms off and on) + autograd gradients
   finetune_steps.npz: depth_fine_tuning.py:261-283 inner loop (model -> zero_grad -> JointLoss ->
                       backward -> step), 3 steps on one pair
 """
@@ -283,16 +285,47 @@ def gen_finetune():
     print("finetune losses", losses)
 
 
+def gen_parameter():
+    """JointLoss with lambda_parameter > 0 (joint_loss.py:34-39 -> parameter_loss.py:13-19) on the unmodified reference."""
+    import loss.joint_loss as jl
+    from oracle import parameter_oracle as po
+    seed, lam = 31, 0.05
+    inits, params = po.make_case(seed)
+    p_init = [torch.tensor(a) for a in inits]
+    ps = [torch.nn.Parameter(torch.tensor(a)) for a in params]
+    jl._dtype = torch.float32
+    opt = types.SimpleNamespace(lambda_view_baseline=0.0, lambda_reprojection=0.0, lambda_parameter=lam)
+    loss, meta = jl.JointLoss(opt, p_init)(None, None, parameters=ps)
+    loss.backward()
+    out = {"lambda": np.float32(lam), "seed": np.int64(seed), "loss": loss.detach().numpy(),
+           "parameter_loss": meta["parameter_loss"].detach().numpy()}
+    for i, p in enumerate(ps):
+        out[f"grad_{i}"] = p.grad.numpy()
+    # combined with the consistency term (the total the fine-tuning loop sees)
+    name = "geo_b2"
+    cseed, pairs, H, W, stress, lr_, lb_ = CONSISTENCY_CASES[name]
+    batch = synth.make_pair_batch(cseed, pairs, H, W, stress=stress)
+    depth = torch.tensor(synth.synth_depth_pred(cseed, len(pairs), H, W))
+    opt2 = types.SimpleNamespace(lambda_view_baseline=lb_, lambda_reprojection=lr_, lambda_parameter=lam)
+    for p in ps:
+        p.grad = None
+    total, meta2 = jl.JointLoss(opt2, p_init)(depth, to_metadata(batch, torch.float32), parameters=ps)
+    out["total_with_geo_b2"] = total.detach().numpy()
+    out["meta_keys"] = np.array(sorted(meta2.keys()))
+    np.savez_compressed(os.path.join(OUT, "parameter_loss.npz"), **out)
+    print("parameter loss", float(loss), "total with consistency", float(total))
+
+
 def main():
     ap = argparse.ArgumentParser(description=__doc__)
-    ap.add_argument("--only", default=None, help="generate one fixture family: consistency|adam|hourglass|finetune|monodepth2|midas|flowmask")
+    ap.add_argument("--only", default=None, help="generate one fixture family: consistency|adam|hourglass|finetune|monodepth2|midas|flowmask|parameter")
     only = ap.parse_args().only
     ref_import.setup()
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     os.makedirs(OUT, exist_ok=True)
     gens = {"consistency": gen_consistency, "adam": gen_adam, "hourglass": gen_hourglass, "finetune": gen_finetune,
-            "monodepth2": gen_monodepth2, "midas": gen_midas, "flowmask": gen_flowmask}
+            "monodepth2": gen_monodepth2, "midas": gen_midas, "flowmask": gen_flowmask, "parameter": gen_parameter}
     for name, fn in gens.items():
         if only is None or only == name:
             fn()

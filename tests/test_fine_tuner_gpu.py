@@ -43,7 +43,14 @@ def test_fine_tune_and_save_depth_end_to_end(tmp_path, resident):
     assert (ft.model.P.flat - w0).abs().max().item() > 0                            # weights moved
     for e in (1, 2):
         ck = torch.load(os.path.join(ft.out_dir, "checkpoints", f"{e:04d}.pth"), map_location="cpu")
-        assert list(ck.keys()) == list(mc_arch.state_dict_shapes().keys())           # reference state_dict keys / order
+        # the reference saves netG.state_dict() of the DataParallel-wrapped hourglass: same keys / order, `module.` prefix
+        assert list(ck.keys()) == ["module." + k for k in mc_arch.state_dict_shapes().keys()]
+    # round trip in both formats: a reference-format checkpoint and a bare HourglassModel state_dict load identically
+    from consistent_depth_b200.monodepth.mannequin_challenge_model import MannequinChallengeModel
+    m2 = MannequinChallengeModel(state_dict=ck)
+    assert torch.equal(m2.P.flat, ft.model.P.flat) and torch.equal(m2.P.buf_flat, ft.model.P.buf_flat)
+    m2.load_state_dict({k[7:]: v for k, v in ck.items()})
+    assert torch.equal(m2.P.flat, ft.model.P.flat)
     ev = os.path.join(ft.out_dir, "eval")
     losses = json.load(open(os.path.join(ev, "loss_e0002_iter000008.json")))
     assert set(losses) == {"reprojection", "disparity", "mean"} and len(losses["reprojection"]) == 4

@@ -1,4 +1,4 @@
-"""GPU, OPT-IN (CVD_TEST_FLOWMASK=1): cvd_flow_consistency_masks against the oracle and the golden masks the reference's
+"""GPU: cvd_flow_consistency_masks against the oracle and the golden masks the reference's
 utils/consistency.py produced.  Opt-in because the kernel was written after the round's GPU budget was spent."""
 import os
 
@@ -8,7 +8,7 @@ import pytest
 from oracle import flowmask_oracle as fo
 from oracle.make_golden import FLOWMASK_CASES
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("CVD_TEST_FLOWMASK") != "1", reason="unvalidated kernel: set CVD_TEST_FLOWMASK=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", list(FLOWMASK_CASES))

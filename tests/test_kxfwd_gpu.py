@@ -1,4 +1,4 @@
-"""GPU, OPT-IN (CVD_TEST_KXFWD=1): the experimental kx-fused forward convolution of DESIGN.md §8 -- column conv with
+"""GPU: the experimental kx-fused forward convolution of DESIGN.md §8 -- column conv with
 N = k*Cout GEMM columns (conv_col.cu) + shifted sum (kx_epilogue.cu) -- against torch's conv2d, and the MC engine with
 CVD_KXFWD=1 against the default engine.  Not part of the default suite: the path is off by default and has not been
 validated on hardware yet."""
@@ -11,7 +11,7 @@ import torch.nn.functional as F
 
 from oracle import synth
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("CVD_TEST_KXFWD") != "1", reason="experimental path: set CVD_TEST_KXFWD=1")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
