@@ -53,8 +53,8 @@ def lib():
         _lib.cvd_launch_count.restype = C.c_longlong
         _lib.cvd_consistency_workspace_bytes.restype = C.c_size_t
         _lib.cvd_conv_packed_bytes.restype = C.c_size_t
-        _lib.cvd_convr_packed_bytes.restype = C.c_size_t
         _lib.cvd_bn_scratch_bytes.restype = C.c_size_t
+        _lib.cvd_conv2_packed_bytes.restype = C.c_size_t
     return _lib
 
 

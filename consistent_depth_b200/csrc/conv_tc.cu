@@ -32,6 +32,7 @@
 #include "cvd_common.cuh"
 #include "tc_common.cuh"
 #include "fill.cuh"
+#include "bn_epilogue.cuh"
 
 namespace {
 
@@ -254,35 +255,7 @@ conv_tc_kernel(const ConvArgs p)
 #pragma unroll
             for (int i = 0; i < 16; ++i) if (c16 + i < p.cout_valid) v[i] += __ldg(p.bias + c16 + i);
           }
-          if (p.st_scratch) {
-            // BatchNorm batch statistics fused into the epilogue: column sums over the warp's 32 pixels by a
-            // transposing butterfly (8+4+2+1+1 shuffles per quantity), accumulated per warp in shared memory.
-            float sv[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) sv[i] = inside ? v[i] : 0.f;
-            float tot[2];
-#pragma unroll
-            for (int qq = 0; qq < 2; ++qq) {
-              float t8[8], t4[4], t2[2];
-              const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float lo_ = qq ? sv[i] * sv[i] : sv[i], hi_ = qq ? sv[8 + i] * sv[8 + i] : sv[8 + i];
-                t8[i] = (b4 ? hi_ : lo_) + __shfl_xor_sync(0xffffffffu, b4 ? lo_ : hi_, 16);
-              }
-#pragma unroll
-              for (int i = 0; i < 4; ++i) t4[i] = (b3 ? t8[4 + i] : t8[i]) + __shfl_xor_sync(0xffffffffu, b3 ? t8[i] : t8[4 + i], 8);
-#pragma unroll
-              for (int i = 0; i < 2; ++i) t2[i] = (b2 ? t4[2 + i] : t4[i]) + __shfl_xor_sync(0xffffffffu, b2 ? t4[i] : t4[2 + i], 4);
-              const float t1 = (b1 ? t2[1] : t2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? t2[0] : t2[1], 2);
-              tot[qq] = t1 + __shfl_xor_sync(0xffffffffu, t1, 1);
-            }
-            if (!(lane & 1)) {                           // 16 lanes hold the 16 distinct columns of this chunk
-              const int col = c16 + ((lane >> 1) & 1) + ((lane >> 2) & 1) * 2 + ((lane >> 3) & 1) * 4 + ((lane >> 4) & 1) * 8;
-              float* ws = sstat + (size_t)q * 2 * p.cout;
-              ws[col] += tot[0]; ws[p.cout + col] += tot[1];
-            }
-          }
+          if (p.st_scratch) bnepi::accumulate16(v, inside, lane, sstat + (size_t)q * 2 * p.cout, p.cout, c16);
           if (!inside || c16 >= p.cout_valid) continue;
           if (do_exp) {
 #pragma unroll
@@ -306,45 +279,10 @@ conv_tc_kernel(const ConvArgs p)
       if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);   // accumulator buffer free for tile ti + 2
     }
     if (p.st_scratch) {
-      // CTA partials -> f64 atomics; the last CTA (ticket) finalises a = gamma*rstd, b = beta - mean*a and the
-      // running statistics exactly as bn_stats_kernel does (hourglass.py:28,40,43,165, train mode)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int et = threadIdx.x - 32 * (kIssuers + 9);
-      for (int c = et; c < p.cout_valid; c += 128) {
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) { s1 += sstat[(size_t)w * 2 * p.cout + c]; s2 += sstat[(size_t)w * 2 * p.cout + p.cout + c]; }
-        atomicAdd(p.st_scratch + 2 * c, (double)s1);
-        atomicAdd(p.st_scratch + 2 * c + 1, (double)s2);
-      }
-      __threadfence();
-      volatile int& last_cta = *reinterpret_cast<volatile int*>(tmem_base_sh + 1);   // (static smem would exceed the 227 KB opt-in)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (et == 0) {
-        unsigned int* ticket = reinterpret_cast<unsigned int*>(p.st_scratch + 2 * 256);
-        last_cta = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-        if (last_cta) *ticket = 0u;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (last_cta) {
-        __threadfence();
-        for (int c = et; c < p.cout_valid; c += 128) {
-          const double sum = __ldcg(p.st_scratch + 2 * c), sq = __ldcg(p.st_scratch + 2 * c + 1);
-          p.st_scratch[2 * c] = 0.0; p.st_scratch[2 * c + 1] = 0.0;
-          const double mean = sum / (double)p.st_count;
-          double var = sq / (double)p.st_count - mean * mean;
-          if (var < 0.0) var = 0.0;
-          const float rs = (float)(1.0 / sqrt(var + (double)p.st_eps));
-          const float g = p.st_gamma ? p.st_gamma[c] : 1.f, be = p.st_beta ? p.st_beta[c] : 0.f;
-          const float av = g * rs;
-          p.st_a[c] = av; p.st_b[c] = be - (float)mean * av; p.st_rstd[c] = rs; p.st_mean[c] = (float)mean;
-          if (p.st_rm) {
-            const double unb = p.st_count > 1 ? var * (double)p.st_count / (double)(p.st_count - 1) : var;
-            p.st_rm[c] = (1.f - p.st_mom) * p.st_rm[c] + p.st_mom * (float)mean;
-            p.st_rv[c] = (1.f - p.st_mom) * p.st_rv[c] + p.st_mom * (float)unb;
-          }
-        }
-      }
+      const bnepi::Stats st{p.st_scratch, p.st_gamma, p.st_beta, p.st_rm, p.st_rv, p.st_a, p.st_b, p.st_rstd, p.st_mean,
+                            p.st_eps, p.st_mom, p.st_count};
+      bnepi::finalize(st, sstat, p.cout, p.cout_valid, threadIdx.x - 32 * (kIssuers + 9),
+                      reinterpret_cast<volatile int*>(tmem_base_sh + 1));   // (static smem would exceed the 227 KB opt-in)
     }
   }
 

@@ -176,12 +176,13 @@ class McEngine:
         import os
         self.multi_stream = os.environ.get("CVD_MULTI_STREAM", "1") == "1"
         self.fuse_bn = os.environ.get("CVD_FUSE_BN", "1") == "1"     # BN batch statistics in the conv epilogue
-        # EXPERIMENTAL (not validated on hardware yet): forward convs with k*Cout <= 256 through the
-        # kx-fused column conv + shifted sum instead of k*k taps of N = Cout
-        self.kxfwd = os.environ.get("CVD_KXFWD", "0") == "1"
-        # EXPERIMENTAL: fork the side streams BEFORE branch 0 is enqueued so that branch 0 overlaps with the others too
-        # (today the side streams wait on the main stream after branch 0's launches); unmeasured, off by default
-        self.fork_first = os.environ.get("CVD_FORK_FIRST", "0") == "1"
+        # fork the side streams BEFORE branch 0 is enqueued so that branch 0 overlaps with the others too
+        # (measured on B200, round 2: 139.0 -> 144.8 frame-pairs/s); CVD_FORK_FIRST=0 restores the old order
+        self.fork_first = os.environ.get("CVD_FORK_FIRST", "1") == "1"
+        # second-generation conv path for the inception convolutions (prep.cu + conv2.cu: operands pre-split once into bf16
+        # hi/lo planes, TMA-fed kx-fused tcgen05 conv for forward and dgrad); CVD_CONV2=0 restores the first-generation kernels.
+        # bf16x3 parity mode only.
+        self.v2 = os.environ.get("CVD_CONV2", "1") == "1" and precision == 3
         self.side_streams = []
         self.pmap, self.grad_flat = params.pmap, params.grad_flat
         self._p, self._g, self._rb = params._p, params._g, params._rb
@@ -194,11 +195,40 @@ class McEngine:
     def _packed(self, cin, cout, k):
         return torch.empty(ops.packed_bytes(cin, cout, k, self.prec), dtype=torch.uint8, device=self.dev)
 
+    # second-generation path helpers ------------------------------------------
+    def _z_of(self, t, h, w):
+        """Operand planes of activation handle t (post BN+ReLU), prepared ONCE per forward however many convs read it."""
+        if getattr(t, "z", None) is None:
+            t.z = ops.z_alloc(self.N, t.C, h, w, self.dev)
+            src, C, z = t.src(), t.C, t.z
+            self.fwd.append(lambda: ops.prep_operand(src, C, z))
+        return t.z
+
+    def _conv2(self, z, zoff, wkey, bkey, dst, cin, cout, k, h, w, wshape=None, bn=None):
+        N = self.N
+        Wt = self._p(wkey, shape=wshape)
+        bias = self._p(bkey, n=cout, shape=(cout,))
+        pk = torch.empty(ops.conv2_packed_bytes(cin, cout, k), dtype=torch.uint8, device=self.dev)
+        self.pack2_fwd.append((Wt, pk, False))
+        self.raw_outputs[wkey[:-7]] = (dst.buf, dst.off, cout)
+        d = ops.make_dst(dst.view())
+        t, rm, rv, gamma, beta, si = bn
+        bns = ops.make_bn(self.conv_scratch[si], t.a, t.b, t.rstd, t.mean, gamma, beta, rm, rv)
+        self.fwd.append(lambda: ops.conv2(z, zoff, pk, bias, d, N, h, w, cin, cout, k, 0, bns if self.train_mode else None))
+
+    def _gz_planes(self, C, h, w, slot):
+        key = (C, h, w, slot)
+        if key not in self._gz:
+            self._gz[key] = ops.z_alloc(self.N, C, h, w, self.dev)
+        return self._gz[key]
+
     def _build_plan(self):
         N, H, W = self.N, self.H, self.W
         self.fwd, self.recs = [], []
         self.raw_outputs = {}
         self.pack_fwd, self.pack_bwd = [], []
+        self.pack2_fwd, self.pack2_bwd = [], []
+        self._gz = {}                    # transient gradient-operand planes shared by all inception blocks, by size
         self.scratch = ops.bn_scratch(self.dev)
         self.conv_scratch = [ops.bn_scratch(self.dev) for _ in range(3)]   # one per concurrently running conv
         self.eval_affine = []            # (a, b, lo, hi, running_mean, running_var, gamma, beta) for eval mode
@@ -227,6 +257,8 @@ class McEngine:
         self._emit_backward()
         self.pack_fwd_tab = ops.make_pack_table(self.pack_fwd, self.dev)
         self.pack_bwd_tab = ops.make_pack_table(self.pack_bwd, self.dev)
+        self.pack2_fwd_tab = ops.make_pack2_table(self.pack2_fwd, self.dev) if self.pack2_fwd else None
+        self.pack2_bwd_tab = ops.make_pack2_table(self.pack2_bwd, self.dev) if self.pack2_bwd else None
 
     # forward helpers ------------------------------------------------------
     def _conv(self, x, wkey, bkey, dst, cin, cout, k, N, h, w, flags=0, wshape=None, bn=None):
@@ -237,17 +269,6 @@ class McEngine:
         self.pack_fwd.append((Wt, pk, False))
         self.raw_outputs[wkey[:-7]] = (dst.buf, dst.off, cout)       # conv prefix -> where its raw output lives
         s, d = x.src(), ops.make_dst(dst.view())
-        if self.kxfwd and bn is not None and k >= 3 and flags == 0 and k * cout <= 256 and cout % 16 == 0 and dst.gap == 0:
-            t, rm, rv, gamma, beta, si = bn
-            bufs = ops.kxfwd_buffers(cin, cout, k, N, h, w, prec, self.dev)
-            dv, scratch, npix = dst.view(), self.conv_scratch[si], N * h * w
-
-            def run_kx():
-                ops.conv_kxfwd(s, Wt, bias, dv, N, h, w, cin, cout, k, prec, bufs)
-                if self.train_mode:
-                    ops.bn_stats(dst.buf, dst.off, cout, npix, scratch, t.a, t.b, t.rstd, t.mean, gamma, beta, rm, rv)
-            self.fwd.append(run_kx)
-            return pk
         bns = None
         if bn is not None:     # (tensor record, running_mean, running_var, gamma, beta, scratch index): fused batch statistics
             t, rm, rv, gamma, beta, si = bn
@@ -296,22 +317,34 @@ class McEngine:
         fuse = self.fuse_bn
         rm1 = self._rb(f"{prefix}.convs.0.1.running_mean", o0 + A)
         rv1 = self._rb(f"{prefix}.convs.0.1.running_var", o0 + A)
-        self._conv(x, f"{prefix}.convs.0.0.weight", f"{prefix}.convs.0.0.bias", _T(buf), cin, o0 + A, 1, N, h, w,
-                   wshape=(o0 + A, cin, 1, 1), bn=(one, rm1, rv1, None, None, 0) if fuse else None)
+        v2 = self.v2 and fuse
+        if v2:
+            self._conv2(self._z_of(x, h, w), 0, f"{prefix}.convs.0.0.weight", f"{prefix}.convs.0.0.bias", _T(buf), cin, o0 + A, 1,
+                        h, w, wshape=(o0 + A, cin, 1, 1), bn=(one, rm1, rv1, None, None, 0))
+        else:
+            self._conv(x, f"{prefix}.convs.0.0.weight", f"{prefix}.convs.0.0.bias", _T(buf), cin, o0 + A, 1, N, h, w,
+                       wshape=(o0 + A, cin, 1, 1), bn=(one, rm1, rv1, None, None, 0) if fuse else None)
         self._stats(one, 0, o0 + A, N * h * w, f"{prefix}.convs.0.1.running_mean", f"{prefix}.convs.0.1.running_var",
                     fused=fuse)
         rmk = self._rb(f"{prefix}.convs.1.4.running_mean", Bt)
         rvk = self._rb(f"{prefix}.convs.1.4.running_var", Bt)
         mids, outs = [], []
         aoff, boff = o0, o0 + A
+        zmid = None
+        if v2:                                                 # the three k x k convs read ONE prepared tensor (a1 | a2 | a3)
+            zmid = self._z_of(sub(o0, A), h, w)
         main_list, branches = self.fwd, []
         for i in range(3):                                     # the three k x k convs are independent: parallel branches
             mid = sub(aoff, As[i])
             self.fwd = []
             ko = boff - (o0 + A)
-            self._conv(mid, f"{prefix}.convs.{i + 1}.3.weight", f"{prefix}.convs.{i + 1}.3.bias", _T(buf, off=boff),
-                       As[i], Bs[i], ks[i], N, h, w,
-                       bn=(one, rmk[ko:ko + Bs[i]], rvk[ko:ko + Bs[i]], None, None, i) if fuse else None)
+            if v2:
+                self._conv2(zmid, (aoff - o0) // 8, f"{prefix}.convs.{i + 1}.3.weight", f"{prefix}.convs.{i + 1}.3.bias",
+                            _T(buf, off=boff), As[i], Bs[i], ks[i], h, w, bn=(one, rmk[ko:ko + Bs[i]], rvk[ko:ko + Bs[i]], None, None, i))
+            else:
+                self._conv(mid, f"{prefix}.convs.{i + 1}.3.weight", f"{prefix}.convs.{i + 1}.3.bias", _T(buf, off=boff),
+                           As[i], Bs[i], ks[i], N, h, w,
+                           bn=(one, rmk[ko:ko + Bs[i]], rvk[ko:ko + Bs[i]], None, None, i) if fuse else None)
             branches.append(self.fwd)
             mids.append(mid)
             outs.append(sub(boff, Bs[i]))
@@ -411,18 +444,30 @@ class McEngine:
                 self.bwd.append(lambda buf=buf, dbuf=dbuf, a=a, b=b, rstd=rstd, mean=mean, bw=bw, dbk=dbk, lo=o0 + A, cnt=Bt, npix=npix:
                                 ops.bn_bwd_reduce(buf, lo, cnt, dbuf, npix, scratch, a, b, rstd, mean, bw, True, dbias=dbk))
                 kbranches = []
+                v2 = self.v2 and self.fuse_bn
+                if v2:      # gradient wrt the k x k convs' raw outputs (BN+ReLU backward), prepared once for the three dgrads
+                    gzk = self._gz_planes(Bt, h, w, 0)
+                    gsrc_all = kout.bnbwd_src()
+                    self.bwd.append(lambda gsrc_all=gsrc_all, gzk=gzk, Bt=Bt: ops.prep_operand(gsrc_all, Bt, gzk))
+                boffs = [sum(Bs[:i]) for i in range(3)]
                 for i in range(3):
                     main_bwd, self.bwd = self.bwd, []
                     Wt = self._p(f"{prefix}.convs.{i + 1}.3.weight")
-                    pkt = self._packed(Bs[i], As[i], ks[i])
-                    self.pack_bwd.append((Wt, pkt, True))
                     gs, xs = outs[i].bnbwd_src(), mids[i].src()
                     dW = self._g(f"{prefix}.convs.{i + 1}.3.weight")
                     self.bwd.append(lambda gs=gs, xs=xs, dW=dW, ci=As[i], co=Bs[i], k=ks[i], h=h, w=w:
                                     ops.conv_wgrad(gs, xs, dW, N, h, w, ci, co, k, prec))
                     d = ops.make_dst(mids[i].dview())
-                    self.bwd.append(lambda gs=gs, pkt=pkt, d=d, ci=Bs[i], co=As[i], k=ks[i], h=h, w=w:
-                                    ops.conv(gs, pkt, None, d, N, h, w, ci, co, k, prec, 0))
+                    if v2:
+                        pkt = torch.empty(ops.conv2_packed_bytes(Bs[i], As[i], ks[i]), dtype=torch.uint8, device=self.dev)
+                        self.pack2_bwd.append((Wt, pkt, True))
+                        self.bwd.append(lambda gzk=gzk, zo=boffs[i] // 8, pkt=pkt, d=d, ci=Bs[i], co=As[i], k=ks[i], h=h, w=w:
+                                        ops.conv2(gzk, zo, pkt, None, d, N, h, w, ci, co, k, 0, None))
+                    else:
+                        pkt = self._packed(Bs[i], As[i], ks[i])
+                        self.pack_bwd.append((Wt, pkt, True))
+                        self.bwd.append(lambda gs=gs, pkt=pkt, d=d, ci=Bs[i], co=As[i], k=ks[i], h=h, w=w:
+                                        ops.conv(gs, pkt, None, d, N, h, w, ci, co, k, prec, 0))
                     kbranches.append([[self.bwd[0]], [self.bwd[1]]])
                     self.bwd = main_bwd
                 # wgrad and dgrad of each of the three convs: six independent kernels
@@ -437,12 +482,20 @@ class McEngine:
                 wg = (lambda gs=gs, xs=xs, dW1=dW1, cin=cin, co=o0 + A, h=h, w=w:
                       ops.conv_wgrad(gs, xs, dW1, N, h, w, cin, co, 1, prec))
                 if x.dbuf is not None:
-                    pkt = self._packed(o0 + A, cin, 1)
-                    self.pack_bwd.append((W1, pkt, True))
                     d = ops.make_dst(x.dview())
                     fl = ops.FLAG_ACCUM if x.grad_written else 0
-                    dg = (lambda gs=gs, pkt=pkt, d=d, fl=fl, ci=o0 + A, co=cin, h=h, w=w:
-                          ops.conv(gs, pkt, None, d, N, h, w, ci, co, 1, prec, fl))
+                    if v2:
+                        gz1 = self._gz_planes(o0 + A, h, w, 1)
+                        pkt = torch.empty(ops.conv2_packed_bytes(o0 + A, cin, 1), dtype=torch.uint8, device=self.dev)
+                        self.pack2_bwd.append((W1, pkt, True))
+                        self.bwd.append(lambda gs=gs, gz1=gz1, c1=o0 + A: ops.prep_operand(gs, c1, gz1))
+                        dg = (lambda gz1=gz1, pkt=pkt, d=d, fl=fl, ci=o0 + A, co=cin, h=h, w=w:
+                              ops.conv2(gz1, 0, pkt, None, d, N, h, w, ci, co, 1, fl, None))
+                    else:
+                        pkt = self._packed(o0 + A, cin, 1)
+                        self.pack_bwd.append((W1, pkt, True))
+                        dg = (lambda gs=gs, pkt=pkt, d=d, fl=fl, ci=o0 + A, co=cin, h=h, w=w:
+                              ops.conv(gs, pkt, None, d, N, h, w, ci, co, 1, prec, fl))
                     self.bwd.append(("par", [[wg], [dg]]))
                     x.grad_written = True
                 else:
@@ -498,6 +551,8 @@ class McEngine:
         assert images.shape == (self.N, 3, self.H, self.W), images.shape
         ops.image_to_nhwc4(images.contiguous(), self.img4, self.N, self.H, self.W)
         ops.pack_batch(self.pack_fwd_tab[0], self.pack_fwd_tab[1], self.prec)
+        if self.pack2_fwd_tab is not None:
+            ops.conv2_pack_batch(*self.pack2_fwd_tab)
         self._run(self.fwd)
         if self.train_mode:
             self.P.num_batches_tracked += 1
@@ -507,4 +562,6 @@ class McEngine:
         """grad_depth (N,H,W): d loss / d depth.  Accumulates into grad_flat (zero it first, as opt.zero_grad does)."""
         self.grad_depth = grad_depth.contiguous()
         ops.pack_batch(self.pack_bwd_tab[0], self.pack_bwd_tab[1], self.prec)
+        if self.pack2_bwd_tab is not None:
+            ops.conv2_pack_batch(*self.pack2_bwd_tab)
         self._run(self.bwd)

@@ -330,26 +330,62 @@ def recip_relu_bwd(ddepth, depth, raw4, draw4):
                                              C.c_longlong(depth.numel()), _lib.stream()), "cvd_recip_relu_bwd")
 
 
-# ---------------------------------------------------------------- experimental kx-fused forward conv (CVD_KXFWD=1)
-def kxfwd_buffers(cin, cout, k, N, H, W, precision, device):
-    """(rearranged weight (k*cout, cin, k, 1), packed blob, column-conv output D (N, H, W+k-1, k*cout))."""
-    kc = k * cout
-    wcol = torch.empty(kc, cin, k, 1, device=device)
-    pk = torch.empty(int(_lib.lib().cvd_convr_packed_bytes(cin, kc, k, 1, precision)), dtype=torch.uint8, device=device)
-    D = torch.empty(N, H, W + k - 1, kc, device=device)
-    return wcol, pk, D
+# ---------------------------------------------------------------- second-generation conv path (prep.cu, conv2.cu)
+def z_alloc(N, C, H, W, device):
+    """Operand planes of a C-channel tensor: [2 (hi | lo)][N][ceil16(C)/8][H*W][8] bf16 (see prep.cu)."""
+    c8 = (C + 15) // 16 * 2
+    return torch.empty(2, N, c8, H * W, 8, dtype=torch.bfloat16, device=device)
 
 
-def conv_kxfwd(src, w_oihw, bias, dst_view, N, H, W, cin, cout, k, precision, bufs):
-    """dst_view (View) = conv_kxk(src) + bias through the column conv (N = k*cout GEMM columns) + shifted sum."""
-    wcol, pk, D = bufs
-    L, st = _lib.lib(), _lib.stream()
-    kc, pad = k * cout, (k - 1) // 2
-    _lib.check(L.cvd_kx_rearrange_weights(_lib.ptr(w_oihw), cin, cout, k, _lib.ptr(wcol), st), "cvd_kx_rearrange_weights")
-    _lib.check(L.cvd_convr_pack_weights(_lib.ptr(wcol), cin, kc, k, 1, precision, _lib.ptr(pk), st), "cvd_convr_pack_weights")
-    d = make_dst(View(D, 0))
-    _lib.check(L.cvd_convr_fwd(C.byref(src), _lib.ptr(pk), None, C.byref(d), N, H, W, W + k - 1, cin, kc, k, 1, pad, pad,
-                               precision, 0, st), "cvd_convr_fwd")
-    assert dst_view.gap == 0 or dst_view.n0 >= cout
-    _lib.check(L.cvd_shift_sum(_lib.ptr(D), kc, _lib.ptr(bias), _lib.ptr(dst_view.t), dst_view.c_total, dst_view.off,
-                               N, H, W, k, cout, st), "cvd_shift_sum")
+def prep_operand(src, Cn, z, zc8_off=0):
+    """Transform + bf16 hi/lo split of the Cn logical channels of `src` (cvd_src_t from make_src) into chunks
+    [zc8_off, zc8_off + ceil16(Cn)/8) of the planes z (from z_alloc)."""
+    N, c8, HW = z.shape[1], z.shape[2], z.shape[3]
+    _lib.check(_lib.lib().cvd_prep_operand(C.byref(src), int(Cn), C.c_longlong(N), C.c_longlong(HW), _lib.ptr(z), c8, zc8_off, 3,
+                                           _lib.stream()), "cvd_prep_operand")
+
+
+def conv2_tap_groups(cout_gemm, k):
+    G, ng = C.c_int(0), C.c_int(0)
+    _lib.check(_lib.lib().cvd_conv2_tap_groups(cout_gemm, k, C.byref(G), C.byref(ng)), "cvd_conv2_tap_groups")
+    return G.value, ng.value
+
+
+def conv2_packed_bytes(cin_gemm, cout_gemm, k):
+    return int(_lib.lib().cvd_conv2_packed_bytes(cin_gemm, cout_gemm, k))
+
+
+def make_pack2_table(entries, device):
+    """entries: [(w_oihw tensor, packed uint8 tensor, flip)] -> device descriptor table for conv2_pack_batch."""
+    import numpy as np
+    dt = np.dtype([("w", "<u8"), ("out", "<u8"), ("cin", "<i4"), ("cout", "<i4"), ("k", "<i4"), ("flip", "<i4"),
+                   ("G", "<i4"), ("ng", "<i4")])
+    arr = np.zeros(len(entries), dtype=dt)
+    for i, (w, out, flip) in enumerate(entries):
+        cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+        G, ng = conv2_tap_groups(cin if flip else cout, k)
+        arr[i] = (w.data_ptr(), out.data_ptr(), cin, cout, k, 1 if flip else 0, G, ng)
+    t = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
+    t._keep = [e[0] for e in entries] + [e[1] for e in entries]
+    return t, len(entries)
+
+
+def conv2_pack_batch(table, n):
+    _lib.check(_lib.lib().cvd_conv2_pack_batch(_lib.ptr(table), n, _lib.stream()), "cvd_conv2_pack_batch")
+
+
+def conv2_pack(w_oihw, flip=False):
+    """One conv's weights -> conv2 tiles (tests / one-off use; engines pack all convs in one launch)."""
+    cout, cin, k, _ = w_oihw.shape
+    gi, go = (cout, cin) if flip else (cin, cout)
+    out = torch.empty(conv2_packed_bytes(gi, go, k), dtype=torch.uint8, device=w_oihw.device)
+    tab, n = make_pack2_table([(w_oihw, out, flip)], w_oihw.device)
+    conv2_pack_batch(tab, n)
+    return out
+
+
+def conv2(z, zc8_off, packed, bias, dst, N, H, W, cin, cout, k, flags=0, bn=None):
+    """TMA-fed kx-fused conv: z operand planes (z_alloc/prep_operand), dst cvd_dst_t; cin/cout in GEMM terms."""
+    _lib.check(_lib.lib().cvd_conv2_fwd(_lib.ptr(z), z.shape[2], zc8_off, _lib.ptr(packed), _lib.ptr(bias), C.byref(dst),
+                                        N, H, W, cin, cout, k, flags, C.byref(bn) if bn is not None else None,
+                                        _lib.stream()), "cvd_conv2_fwd")

@@ -180,6 +180,31 @@ int cvd_conv_fwd_bn(const cvd_src_t* src, const void* packed_w, const float* bia
                     const cvd_dst_t* dst, int N, int H, int W, int cin, int cout, int k,
                     int precision, int flags, const cvd_bn_t* bn, void* stream);
 
+/* ---- second-generation conv path: pre-split operands + TMA-fed, kx-fused tcgen05 conv (csrc/prep.cu, conv2.cu) ----
+ * cvd_prep_operand applies the per-channel transform of `src` (CVD_XF_AFFINE: BatchNorm+ReLU of the producer,
+ * hourglass.py:28-29; CVD_XF_BNBWD: its backward) ONCE and writes the result as two bf16 planes (v = hi + lo) in the
+ * chunk-planar layout  z[plane][n][c/8][y*W+x][c%8]  -- the layout a TMA box load turns into the UMMA shared-memory
+ * operand.  The C logical channels of the view become dense channels [8*zc8_off, 8*zc8_off + ceil16(C)) of z, whose
+ * planes hold zc8 chunks per image.  z bytes: 2 * N * zc8 * HW * 16. */
+int cvd_prep_operand(const cvd_src_t* src, int C, long long N, long long HW, void* z, int zc8, int zc8_off,
+                     int precision, void* stream);
+
+/* Weight tiles of the kx-fused conv.  G horizontal taps share one GEMM-N block (N = G * ceil16(cout_gemm) <= 256);
+ * cvd_conv2_tap_groups reports (G, number of groups).  cvd_conv2_pack_batch packs n convolutions in one launch from a
+ * device table of { const float* w_oihw; void* packed; int cin, cout, k, flip, G, ng } (40 bytes; cin/cout = the OIHW
+ * extents, flip = 1 builds the dgrad operand: channels swapped, taps rotated 180 degrees). */
+int cvd_conv2_tap_groups(int cout_gemm, int k, int* G, int* ng);
+size_t cvd_conv2_packed_bytes(int cin_gemm, int cout_gemm, int k);
+int cvd_conv2_pack_batch(const void* descs_dev, int n, void* stream);
+
+/* Convolution (stride 1, "same"), replaces nn.Conv2d forward (hourglass.py:27,39,42) and, with flip-packed weights and a
+ * CVD_XF_BNBWD-prepared operand, its input gradient.  z / zc8 / zc8_off: operand planes from cvd_prep_operand (the conv
+ * reads ceil16(cin) channels from chunk zc8_off); cin / cout in GEMM terms; bias, dst, flags, bn as cvd_conv_fwd(_bn)
+ * (bn may be NULL).  bf16x3 split precision (fp32-class) only. */
+int cvd_conv2_fwd(const void* z, int zc8, int zc8_off, const void* packed_w, const float* bias,
+                  const cvd_dst_t* dst, int N, int H, int W, int cin, int cout, int k,
+                  int flags, const cvd_bn_t* bn, void* stream);
+
 /* Weight gradient of one channel chunk of a grouped convolution (see cvd_conv_pack_weights): gsrc / xsrc are views
  * of the chunk's c output / input channels, dw points at the chunk's rows of the (Cout, group_size, k, k) gradient. */
 int cvd_conv_wgrad_grouped(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_ogkk,
@@ -332,23 +357,6 @@ int cvd_up2_bilinear_bwd(const float* dout, int N, int h, int w, int C, int alig
 int cvd_recip_relu_fwd(const float* raw4, float* depth, long long n, void* stream);
 int cvd_recip_relu_bwd(const float* ddepth, const float* depth, const float* raw4, float* draw4, long long n, void* stream);
 
-/* ------------------------------------------------------------------------------------------------
- * EXPERIMENTAL (off unless CVD_KXFWD=1): kx-fused forward convolution for layers with few output
- * channels.  A k x k conv with Cout outputs = a k x 1 column conv with k*Cout GEMM columns
- *   D[n, y, x', kx*Cout + co] = sum_{ky, ci} X[n, y + ky - pad, x' - pad, ci] * W[co, ci, ky, kx],  x' in [0, W + k - 1)
- * (cvd_convr_fwd with kh = k, kw = 1, pad_y = pad_x = pad, Wout = W + k - 1 on weights rearranged by
- * cvd_kx_rearrange_weights and packed by cvd_convr_pack_weights) followed by
- *   out[n, y, x, co] = bias[co] + sum_kx D[n, y, x + kx, kx*Cout + co]                    (cvd_shift_sum).
- * cvd_convr_fwd is cvd_conv_fwd generalised to kh x kw filters, separate paddings and an output wider than the input.
- * ------------------------------------------------------------------------------------------------ */
-size_t cvd_convr_packed_bytes(int cin, int cout, int kh, int kw, int precision);
-int cvd_convr_pack_weights(const float* w_oihw, int cin, int cout, int kh, int kw, int precision, void* packed, void* stream);
-int cvd_kx_rearrange_weights(const float* w_oihw, int cin, int cout, int k, float* w_col, void* stream);
-int cvd_convr_fwd(const cvd_src_t* src, const void* packed_w, const float* bias, const cvd_dst_t* dst,
-                  int N, int H, int W, int Wout, int cin, int cout, int kh, int kw, int pad_y, int pad_x,
-                  int precision, int flags, void* stream);
-int cvd_shift_sum(const float* D, int d_ctotal, const float* bias, float* out, int o_ctotal, int o_coff,
-                  int N, int H, int W, int k, int cout, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SURVEY §8(f) rank 3 (not yet validated on hardware): the flow + photometric consistency masks of

@@ -22,10 +22,11 @@ import torch
 import torch.nn.functional as F
 
 
-def pixel_grid(batch_size, shape, dtype):
+def pixel_grid(batch_size, shape, dtype, device=None):
+    # the reference creates these on utils.torch_helpers._device; here: wherever the depths live
     H, W = shape
-    x = torch.linspace(0, W - 1, W, dtype=dtype)
-    y = torch.linspace(0, H - 1, H, dtype=dtype)
+    x = torch.linspace(0, W - 1, W, dtype=dtype, device=device)
+    y = torch.linspace(0, H - 1, H, dtype=dtype, device=device)
     Y, X = torch.meshgrid(y, x, indexing="ij")
     return torch.stack((X, Y), dim=0)[None].expand(batch_size, -1, -1, -1)
 
@@ -35,7 +36,7 @@ def pixels_to_rays(pixels, intrinsics):
     uvs = pixels - intrinsics[:, 2:].view(-1, 2, 1, 1)
     uvs = torch.stack((uvs[:, 0], -uvs[:, 1]), dim=1)
     fxys = intrinsics[:, :2].view(-1, 2, 1, 1)
-    return torch.cat((uvs / fxys, -torch.ones((B, 1, H, W), dtype=uvs.dtype)), dim=1)
+    return torch.cat((uvs / fxys, -torch.ones((B, 1, H, W), dtype=uvs.dtype, device=uvs.device)), dim=1)
 
 
 def project(points, intrinsics):
@@ -55,7 +56,7 @@ def reproject_points(points_cam_ref, extrinsics_ref, extrinsics_tgt):
 
 def sample(data, uv):
     H, W = data.shape[2:]
-    size = torch.tensor((W - 1, H - 1), dtype=uv.dtype).view(1, -1, 1, 1)
+    size = torch.tensor((W - 1, H - 1), dtype=uv.dtype, device=uv.device).view(1, -1, 1, 1)
     grid = (2 * uv / size - 1).permute(0, 2, 3, 1)
     return F.grid_sample(data, grid, padding_mode="border", align_corners=False)
 
@@ -71,7 +72,7 @@ def consistency_loss(depths, extrinsics, intrinsics, flows, masks,
     """depths (B,2,H,W) -> (loss shape (1,), {"reprojection": (B,), "disparity": (B,)})."""
     B, N, H, W = depths.shape
     dtype = depths.dtype
-    pixels = pixel_grid(B * N, (H, W), dtype)
+    pixels = pixel_grid(B * N, (H, W), dtype, depths.device)
     rays = pixels_to_rays(pixels, intrinsics.reshape(B * N, 4))
     points_cam = (rays * depths.reshape(B * N, 1, H, W)).reshape(B, N, 3, H, W)
     pixels = pixels.reshape(B, N, 2, H, W)
@@ -90,10 +91,10 @@ def consistency_loss(depths, extrinsics, intrinsics, flows, masks,
             disp_diff = 1.0 / points_cam_tgt[:, -1:] - 1.0 / warped[:, -1:]
             disp_losses.append(f * weighted_mean_loss(torch.abs(disp_diff), masks[k]))
     reproj = (lambda_reprojection * torch.mean(torch.stack(reproj_losses, -1), -1)
-              if reproj_losses else torch.zeros(B, dtype=dtype))
+              if reproj_losses else torch.zeros(B, dtype=dtype, device=depths.device))
     disp = (lambda_view_baseline * torch.mean(torch.stack(disp_losses, -1), -1)
-            if disp_losses else torch.zeros(B, dtype=dtype))
-    loss = torch.zeros(1, dtype=dtype) + torch.mean(reproj + disp)
+            if disp_losses else torch.zeros(B, dtype=dtype, device=depths.device))
+    loss = torch.zeros(1, dtype=dtype, device=depths.device) + torch.mean(reproj + disp)
     return loss, {"reprojection": reproj, "disparity": disp}
 
 

@@ -181,6 +181,10 @@ def test_network_parity_at_bench_resolution():
     lref.backward()
     worst_n = 0.0
     for k in ho.trainable_keys():
+        # a conv bias in front of a BatchNorm has an exactly-zero true gradient (the batch mean removes it): what either
+        # implementation reports there is rounding noise, so only weights and the un-normalised head are compared
+        if k.endswith(".bias") and k != "pred_layer.bias":
+            continue
         ref = P[k].grad.double()
         got = model.P._g(k).cpu().double().reshape(ref.shape)
         rn, gn = float(ref.norm()), float(got.norm())

@@ -15,7 +15,7 @@ class _Recorder:
         self.real, self.calls, self.args = real, collections.Counter(), collections.defaultdict(list)
 
     def __getattr__(self, name):
-        if name in ("cvd_bn_scratch_bytes", "cvd_conv_packed_bytes", "cvd_convr_packed_bytes", "cvd_correlation_out_size"):
+        if name in ("cvd_bn_scratch_bytes", "cvd_conv_packed_bytes", "cvd_conv2_packed_bytes", "cvd_correlation_out_size"):
             return getattr(self.real, name)
 
         def f(*a):
@@ -55,6 +55,7 @@ def _check_weight_coverage(P, arch, rec, chunk_rows=None):
             assert all(targets[g[r:r + 1].data_ptr()] == 1 for r in rows), k
         else:
             assert targets[g.data_ptr()] == 1, k
+
     dead = [P._g(k).data_ptr() for k in P.pmap if arch.dead_parameter(k)]
     assert not any(targets[p] for p in dead)
 
@@ -99,22 +100,6 @@ def test_midas_plan(fake_lib):
     _check_weight_coverage(P, midas_arch, fake_lib, chunk_rows=CHUNK)
 
 
-def test_kx_fused_forward_call_sequence(fake_lib):
-    """Experimental path: rearrange -> pack -> column conv (kh = k, kw = 1, Wout = W + k - 1, N = k*Cout) -> shifted sum."""
-    from consistent_depth_b200 import ops
-    N, H, W, cin, cout, k = 2, 8, 12, 64, 16, 11
-    x, y = torch.zeros(N, H, W, cin), torch.zeros(N, H, W, 48)
-    w, bias = torch.zeros(cout, cin, k, k), torch.zeros(cout)
-    bufs = ops.kxfwd_buffers(cin, cout, k, N, H, W, 3, "cpu")
-    assert bufs[0].shape == (k * cout, cin, k, 1) and bufs[2].shape == (N, H, W + k - 1, k * cout)
-    ops.conv_kxfwd(ops.make_src(ops.View(x, 0)), w, bias, ops.View(y, 16), N, H, W, cin, cout, k, 3, bufs)
-    assert [n for n in fake_lib.calls] == ["cvd_kx_rearrange_weights", "cvd_convr_pack_weights", "cvd_convr_fwd", "cvd_shift_sum"]
-    a = fake_lib.args["cvd_convr_fwd"][0]
-    assert a[4:14] == (N, H, W, W + k - 1, cin, k * cout, k, 1, 5, 5)
-    s = fake_lib.args["cvd_shift_sum"][0]
-    assert s[1] == k * cout and s[4:] [:7] == (48, 16, N, H, W, k, cout)
-
-
 def test_flownet2_op_modules_plumbing(fake_lib):
     """Correlation / Resample2d / ChannelNorm mirrors: constructor surface of the reference modules, output shapes
     (cvd_correlation_out_size is host-only code and runs for real), argument order of the launches."""
@@ -142,11 +127,23 @@ def test_mannequin_challenge_plan(fake_lib):
     assert e.forward(torch.rand(2, 3, 32, 48)).shape == (2, 32, 48)
     n_inc = sum(1 for k in mc_arch.state_dict_shapes() if k.endswith(".convs.0.0.weight"))
     assert n_inc == 22
-    fwd_convs = fake_lib.calls["cvd_conv_fwd"] + fake_lib.calls["cvd_conv_fwd_bn"]
-    assert fwd_convs == 1 + 4 * n_inc + 1                      # conv1 + (fused 1x1 + three k x k) per inception + pred layer
+    # conv1 and the pred layer (3 / 1 channels) stay on the first-generation kernel; every inception conv (fused 1x1 + three
+    # k x k) runs the TMA-fed kx-fused kernel on operands prepared once: the block input (unless another block already
+    # prepared the same tensor) and the 1x1 outputs a1|a2|a3
+    assert fake_lib.calls["cvd_conv_fwd"] + fake_lib.calls["cvd_conv_fwd_bn"] == 2
+    assert fake_lib.calls["cvd_conv2_fwd"] == 4 * n_inc
+    assert n_inc < fake_lib.calls["cvd_prep_operand"] <= 2 * n_inc
+    assert fake_lib.calls["cvd_conv2_pack_batch"] == 1
+    fwd_convs = 2 + 4 * n_inc
     assert fake_lib.calls["cvd_bn_stats"] == 0                 # statistics come from the conv epilogues
+    n_prep_fwd = fake_lib.calls["cvd_prep_operand"]
     e.backward(torch.rand(2, 32, 48))
     assert fake_lib.calls["cvd_conv_wgrad"] == fwd_convs
+    # backward: one gradient-operand preparation per BatchNorm group (k x k outputs, 1x1 outputs), dgrads on the new kernel
+    # (4 per inception) except the pred layer's; conv1 has no input gradient
+    assert fake_lib.calls["cvd_prep_operand"] - n_prep_fwd == 2 * n_inc
+    assert fake_lib.calls["cvd_conv2_fwd"] == 8 * n_inc
+    assert fake_lib.calls["cvd_conv_fwd"] + fake_lib.calls["cvd_conv_fwd_bn"] == 3
     targets = _wgrad_targets(fake_lib)
     for k, (off, shape) in P.pmap.items():
         if len(shape) != 4:
@@ -158,18 +155,11 @@ def test_mannequin_challenge_plan(fake_lib):
             assert targets[g.data_ptr()] == 1, k
 
 
-def test_mannequin_challenge_plan_with_experimental_kx_forward(fake_lib, monkeypatch):
-    """CVD_KXFWD=1: exactly the forward convs with k >= 3 and k * Cout <= 256 take the column-conv route,
-    each followed by the shifted sum and a separate BatchNorm statistics pass; everything else is unchanged."""
-    from consistent_depth_b200.monodepth import mc_arch
+def test_mannequin_challenge_plan_first_generation_kernels(fake_lib, monkeypatch):
+    """CVD_CONV2=0: every conv on the first-generation kernel (the fallback kept for A/B measurements)."""
     from consistent_depth_b200.monodepth.mc_engine import McEngine, McParams
-    monkeypatch.setenv("CVD_KXFWD", "1")
+    monkeypatch.setenv("CVD_CONV2", "0")
     e = McEngine(McParams("cpu"), 2, 32, 48)
-    assert e.kxfwd
     e.forward(torch.rand(2, 3, 32, 48))
-    eligible = [k for k, s in mc_arch.state_dict_shapes().items()
-                if len(s) == 4 and ".convs." in k and k.endswith(".3.weight") and s[2] >= 3 and s[2] * s[0] <= 256 and s[0] % 16 == 0]
-    assert len(eligible) > 30
-    for name in ("cvd_kx_rearrange_weights", "cvd_convr_pack_weights", "cvd_convr_fwd", "cvd_shift_sum", "cvd_bn_stats"):
-        assert fake_lib.calls[name] == len(eligible), name
-    assert fake_lib.calls["cvd_conv_fwd"] + fake_lib.calls["cvd_conv_fwd_bn"] == 90 - len(eligible)
+    assert fake_lib.calls["cvd_conv_fwd"] + fake_lib.calls["cvd_conv_fwd_bn"] == 1 + 4 * 22 + 1
+    assert fake_lib.calls["cvd_conv2_fwd"] == 0 and fake_lib.calls["cvd_prep_operand"] == 0
