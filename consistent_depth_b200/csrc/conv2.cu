@@ -34,6 +34,8 @@ namespace {
 
 constexpr int kThreads = 32 * 7;
 constexpr int kMaxA = 4, kMaxB = 32;
+constexpr int kAPad = 256;                     // zeroed bytes behind every A stage: a zero-weight (padded) tap of the last
+                                               // window row reads up to G slots past the stage and must not meet NaN / Inf garbage
 constexpr int kOPitch = 20;                    // floats per obuf row (16 + 4: conflict-free float4 access)
 
 struct C2Args {
@@ -65,8 +67,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
 {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* a_ring = smem;                                                      // NA x a_stage_bytes (+1 KB guard)
-  uint8_t* b_ring = a_ring + (size_t)p.NA * p.a_stage_bytes + 1024;            // NB x b_tile_bytes
+  uint8_t* a_ring = smem;                                                      // NA x (a_stage_bytes + kAPad)
+  uint8_t* b_ring = a_ring + (size_t)p.NA * (p.a_stage_bytes + kAPad);          // NB x b_tile_bytes
   float* obuf = reinterpret_cast<float*>(b_ring + (size_t)p.NB * p.b_tile_bytes);   // [128][kOPitch]
   float* sstat = obuf + 128 * kOPitch;                                         // [4][2][Cp]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 8 * p.Cp);
@@ -80,6 +82,9 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.st.scratch) for (int i = threadIdx.x; i < 8 * p.Cp; i += kThreads) sstat[i] = 0.f;
+  for (int i = threadIdx.x; i < p.NA * (kAPad / 16); i += kThreads)
+    *reinterpret_cast<uint4*>(a_ring + (size_t)(i / (kAPad / 16)) * (p.a_stage_bytes + kAPad) + p.a_stage_bytes + (i % (kAPad / 16)) * 16) = make_uint4(0u, 0u, 0u, 0u);
+  tc::fence_proxy_async_smem();
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.NA; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.NB; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
@@ -107,7 +112,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
           if (it >= p.NA) tc::mbar_wait(&a_empty[slot], (uint32_t)(((it / p.NA) - 1) & 1));
           tc::mbar_arrive_expect_tx(&a_full[slot], (uint32_t)p.a_stage_bytes);
           // box = (2*WS u64 per row, WR rows, 2 chunks, 1 image, 2 planes): [hi c0][hi c1][lo c0][lo c1], each [row][slot][16 B]
-          tma_load_5d(a_ring + (size_t)slot * p.a_stage_bytes, &zmap, 2 * ix0, iy0, p.zc8_off + 2 * kb, n, 0, &a_full[slot]);
+          tma_load_5d(a_ring + (size_t)slot * (p.a_stage_bytes + kAPad), &zmap, 2 * ix0, iy0, p.zc8_off + 2 * kb, n, 0, &a_full[slot]);
         }
       }
     }
@@ -151,7 +156,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
         const int slot = it % p.NA;
         tc::mbar_wait(&a_full[slot], (uint32_t)((it / p.NA) & 1));
         tc::tc_fence_after();
-        const uint32_t sa = a_base + (uint32_t)slot * p.a_stage_bytes;
+        const uint32_t sa = a_base + (uint32_t)slot * (uint32_t)(p.a_stage_bytes + kAPad);
         for (int ky = 0; ky < p.k; ++ky) {
           for (int g = 0; g < p.ng; ++g, ++bt) {
             int st;
@@ -385,12 +390,15 @@ extern "C" int cvd_conv2_fwd(const void* z, int zc8, int zc8_off, const void* pa
                         bn->eps, bn->momentum, (long long)N * H * W};
   }
   // ---- window geometry
+  int flat_ws = 0;
   if (k == 1) {
     // flattened image: rows of WS slots (largest WS dividing H*W so that no row straddles two images)
-    int ws = 128;
-    while (ws > 8 && (p.HW % ws) != 0) ws >>= 1;
-    CVD_CHECK_ARG(p.HW % ws == 0, "cvd_conv2_fwd: H*W must be a multiple of 8");
-    p.WS = ws; p.Wv = ws; p.Hv = (int)(p.HW / ws);
+    flat_ws = 128;
+    while (flat_ws > 8 && (p.HW % flat_ws) != 0) flat_ws >>= 1;
+    if (p.HW % flat_ws != 0) flat_ws = 0;            // tiny odd-sized maps: the general 2-D window path below
+  }
+  if (flat_ws) {
+    p.WS = flat_ws; p.Wv = flat_ws; p.Hv = (int)(p.HW / flat_ws);
   } else {
     p.Wv = W; p.Hv = H;
     p.WS = (W + k - 1 <= 32) ? 32 : 64;
@@ -413,18 +421,18 @@ extern "C" int cvd_conv2_fwd(const void* z, int zc8, int zc8_off, const void* pa
     p.MT = mt; p.TR = mt * p.R; p.WR = p.TR + k - 1;
     p.plane_bytes = p.WR * p.WS * 16; p.a_stage_bytes = 4 * p.plane_bytes;
     p.b_tile_bytes = 64 * p.Ncols; p.b_tiles = p.nkb * k * p.ng;
-    const size_t fixed = 1024 + 128 * kOPitch * 4 + 8 * p.Cp * 4 + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64 + 1024;
+    const size_t fixed = 128 * kOPitch * 4 + 8 * p.Cp * 4 + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64 + 1024;
     // weights resident in shared memory (1x1 convolutions): loaded once per CTA
     const size_t res_bytes = (size_t)p.b_tiles * p.b_tile_bytes;
     const bool allow_res = !(getenv("CVD2_NO_RESIDENT") && getenv("CVD2_NO_RESIDENT")[0] == '1');
-    if (allow_res && p.b_tiles <= kMaxB && fixed + res_bytes + 2 * (size_t)p.a_stage_bytes <= (size_t)smem_budget) {
+    if (allow_res && p.b_tiles <= kMaxB && fixed + res_bytes + 2 * (size_t)(p.a_stage_bytes + kAPad) <= (size_t)smem_budget) {
       p.b_resident = 1; p.NB = p.b_tiles;
-      int na = (int)((smem_budget - fixed - res_bytes) / p.a_stage_bytes);
+      int na = (int)((smem_budget - fixed - res_bytes) / (p.a_stage_bytes + kAPad));
       p.NA = na > kMaxA ? kMaxA : na;
       found = true; break;
     }
     for (int na = 2; na >= 1 && !found; --na) {
-      const long long left = (long long)smem_budget - (long long)fixed - (long long)na * p.a_stage_bytes;
+      const long long left = (long long)smem_budget - (long long)fixed - (long long)na * (p.a_stage_bytes + kAPad);
       int nb = (int)(left / p.b_tile_bytes);
       if (nb > 6) nb = 6;
       if (nb >= 2) { p.b_resident = 0; p.NA = na; p.NB = nb; found = true; }
@@ -454,7 +462,7 @@ extern "C" int cvd_conv2_fwd(const void* z, int zc8, int zc8_off, const void* pa
   CVD_CHECK_ARG(cr == CUDA_SUCCESS, "cvd_conv2_fwd: cuTensorMapEncodeTiled failed (%d) [Wv=%d Hv=%d zc8=%d N=%d WS=%d WR=%d]",
                 (int)cr, p.Wv, p.Hv, zc8, N, p.WS, p.WR);
 
-  const size_t smem = (size_t)p.NA * p.a_stage_bytes + 1024 + (size_t)p.NB * p.b_tile_bytes + 128 * kOPitch * 4 + 8 * p.Cp * 4 +
+  const size_t smem = (size_t)p.NA * (p.a_stage_bytes + kAPad) + (size_t)p.NB * p.b_tile_bytes + 128 * kOPitch * 4 + 8 * p.Cp * 4 +
                       (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64;
   const long long grid = p.ntiles < cvd_num_sms() ? p.ntiles : cvd_num_sms();
   static bool cfg = false;

@@ -183,6 +183,7 @@ class McEngine:
         # hi/lo planes, TMA-fed kx-fused tcgen05 conv for forward and dgrad); CVD_CONV2=0 restores the first-generation kernels.
         # bf16x3 parity mode only.
         self.v2 = os.environ.get("CVD_CONV2", "1") == "1" and precision == 3
+        self.v2_wgrad = self.v2 and os.environ.get("CVD_WGRAD2", "1") == "1"       # weight gradients on the same operand planes
         self.side_streams = []
         self.pmap, self.grad_flat = params.pmap, params.grad_flat
         self._p, self._g, self._rb = params._p, params._g, params._rb
@@ -336,6 +337,7 @@ class McEngine:
         main_list, branches = self.fwd, []
         for i in range(3):                                     # the three k x k convs are independent: parallel branches
             mid = sub(aoff, As[i])
+            mid.zsrc = (zmid, (aoff - o0) // 8)                # where this conv's input lives in the prepared planes
             self.fwd = []
             ko = boff - (o0 + A)
             if v2:
@@ -455,8 +457,14 @@ class McEngine:
                     Wt = self._p(f"{prefix}.convs.{i + 1}.3.weight")
                     gs, xs = outs[i].bnbwd_src(), mids[i].src()
                     dW = self._g(f"{prefix}.convs.{i + 1}.3.weight")
-                    self.bwd.append(lambda gs=gs, xs=xs, dW=dW, ci=As[i], co=Bs[i], k=ks[i], h=h, w=w:
-                                    ops.conv_wgrad(gs, xs, dW, N, h, w, ci, co, k, prec))
+                    if v2 and self.v2_wgrad:
+                        zmid, xo = mids[i].zsrc
+                        self.bwd.append(lambda zmid=zmid, xo=xo, gzk=gzk, go=boffs[i] // 8, gs=gs, xs=xs, dW=dW, ci=As[i], co=Bs[i], k=ks[i], h=h, w=w:
+                                        ops.conv2_wgrad(zmid, xo, gzk, go, dW, N, h, w, ci, co, k) or
+                                        ops.conv_wgrad(gs, xs, dW, N, h, w, ci, co, k, prec))
+                    else:
+                        self.bwd.append(lambda gs=gs, xs=xs, dW=dW, ci=As[i], co=Bs[i], k=ks[i], h=h, w=w:
+                                        ops.conv_wgrad(gs, xs, dW, N, h, w, ci, co, k, prec))
                     d = ops.make_dst(mids[i].dview())
                     if v2:
                         pkt = torch.empty(ops.conv2_packed_bytes(Bs[i], As[i], ks[i]), dtype=torch.uint8, device=self.dev)
@@ -481,14 +489,19 @@ class McEngine:
                 gs, xs = one.bnbwd_src(), x.src()
                 wg = (lambda gs=gs, xs=xs, dW1=dW1, cin=cin, co=o0 + A, h=h, w=w:
                       ops.conv_wgrad(gs, xs, dW1, N, h, w, cin, co, 1, prec))
+                if v2:                                             # gradient wrt the fused 1x1 outputs, prepared once
+                    gz1 = self._gz_planes(o0 + A, h, w, 1)
+                    self.bwd.append(lambda gs=gs, gz1=gz1, c1=o0 + A: ops.prep_operand(gs, c1, gz1))
+                    if self.v2_wgrad:
+                        wg = (lambda xz=x.z, gz1=gz1, gs=gs, xs=xs, dW1=dW1, cin=cin, co=o0 + A, h=h, w=w:
+                              ops.conv2_wgrad(xz, 0, gz1, 0, dW1, N, h, w, cin, co, 1) or
+                              ops.conv_wgrad(gs, xs, dW1, N, h, w, cin, co, 1, prec))
                 if x.dbuf is not None:
                     d = ops.make_dst(x.dview())
                     fl = ops.FLAG_ACCUM if x.grad_written else 0
                     if v2:
-                        gz1 = self._gz_planes(o0 + A, h, w, 1)
                         pkt = torch.empty(ops.conv2_packed_bytes(o0 + A, cin, 1), dtype=torch.uint8, device=self.dev)
                         self.pack2_bwd.append((W1, pkt, True))
-                        self.bwd.append(lambda gs=gs, gz1=gz1, c1=o0 + A: ops.prep_operand(gs, c1, gz1))
                         dg = (lambda gz1=gz1, pkt=pkt, d=d, fl=fl, ci=o0 + A, co=cin, h=h, w=w:
                               ops.conv2(gz1, 0, pkt, None, d, N, h, w, ci, co, 1, fl, None))
                     else:

@@ -389,3 +389,14 @@ def conv2(z, zc8_off, packed, bias, dst, N, H, W, cin, cout, k, flags=0, bn=None
     _lib.check(_lib.lib().cvd_conv2_fwd(_lib.ptr(z), z.shape[2], zc8_off, _lib.ptr(packed), _lib.ptr(bias), C.byref(dst),
                                         N, H, W, cin, cout, k, flags, C.byref(bn) if bn is not None else None,
                                         _lib.stream()), "cvd_conv2_fwd")
+
+
+def conv2_wgrad(xz, x_off, gz, g_off, dw, N, H, W, cin, cout, k):
+    """dw (fp32 OIHW, pre-zeroed or accumulating) += G (x) X on operand planes.  Returns False when the shape is not
+    covered by the second-generation kernel (the caller then runs conv_wgrad on the fp32 views)."""
+    rc = _lib.lib().cvd_conv2_wgrad(_lib.ptr(xz), xz.shape[2], x_off, _lib.ptr(gz), gz.shape[2], g_off, _lib.ptr(dw),
+                                    N, H, W, cin, cout, k, _lib.stream())
+    if rc == 2:
+        return False
+    _lib.check(rc, "cvd_conv2_wgrad")
+    return True

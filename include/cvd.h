@@ -205,6 +205,15 @@ int cvd_conv2_fwd(const void* z, int zc8, int zc8_off, const void* packed_w, con
                   const cvd_dst_t* dst, int N, int H, int W, int cin, int cout, int k,
                   int flags, const cvd_bn_t* bn, void* stream);
 
+/* Weight gradient on the pre-split operand planes (csrc/wgrad2.cu): dW (fp32 OIHW [cout][cin][k][k], RED-accumulated,
+ * caller zeroes it) += sum over pixels of G (x) X, with xz the planes of the conv's INPUT as the forward saw it (cin
+ * channels from chunk x_off; the planes cvd_conv2_fwd read) and gz the planes of the gradient wrt the conv's raw output
+ * (cout channels from chunk g_off; the planes the dgrad cvd_conv2_fwd reads).  TMA-fed; kx taps fused into GEMM N, ky taps
+ * stacked into GEMM M.  Returns 0 = launched, 1 = error, 2 = shape not covered (cin not 16/32/64/128 for k > 1, ...):
+ * the caller then uses cvd_conv_wgrad. */
+int cvd_conv2_wgrad(const void* xz, int xc8, int x_off, const void* gz, int gc8, int g_off, float* dw_oihw,
+                    int N, int H, int W, int cin, int cout, int k, void* stream);
+
 /* Weight gradient of one channel chunk of a grouped convolution (see cvd_conv_pack_weights): gsrc / xsrc are views
  * of the chunk's c output / input channels, dw points at the chunk's rows of the (Cout, group_size, k, k) gradient. */
 int cvd_conv_wgrad_grouped(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_ogkk,

@@ -154,3 +154,49 @@ def test_conv2_bench_layer_shapes_cropped():
         ref = F.conv2d(x.double(), w.double(), None, padding=(k - 1) // 2)
         err = (y.permute(0, 3, 1, 2).double() - ref).abs().max().item()
         assert err <= 6e-5 * ref.abs().max().item(), (cin, cout, k, err)
+
+
+WG_SHAPES = [
+    # cin, cout, k, N, H, W
+    (64, 16, 11, 1, 20, 40),         # M = 2 ky rows x 64 ch, N = 96, three passes of 2 ky groups
+    (64, 16, 11, 2, 33, 130),        # several column tiles (ragged), odd row count
+    (32, 32, 7, 2, 24, 40),          # M = 4 ky rows x 32 ch, N = 64: one pass
+    (64, 32, 7, 1, 16, 24),
+    (32, 64, 5, 1, 20, 28),          # more output than input channels: 8 G chunks
+    (64, 64, 11, 1, 14, 24),         # ky group split over two passes (8 chunks x 96 columns > 512)
+    (32, 16, 3, 1, 12, 20),
+    (128, 208, 1, 1, 32, 48),        # 1x1: K = flattened pixels, N = 208
+    (256, 160, 1, 2, 16, 24),        # two M blocks
+    (256, 256, 1, 1, 14, 24),        # H*W = 336: ragged last K tile
+    (128, 112, 1, 1, 8, 12),
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,N,H,W", WG_SHAPES)
+def test_conv2_wgrad_matches_autograd(cin, cout, k, N, H, W):
+    from consistent_depth_b200 import ops
+    x = rnd(40 + cin + k, (N, cin, H, W))
+    g = rnd(50 + cout + k, (N, cout, H, W))
+    ref = torch.nn.grad.conv2d_weight(x.double(), (cout, cin, k, k), g.double(), padding=(k - 1) // 2)
+    # operands inside wider planes at non-zero chunk offsets, as the engine uses them
+    xz = ops.z_alloc(N, cin + 32, H, W, DEV); gz = ops.z_alloc(N, cout + 16, H, W, DEV)
+    xz.zero_(); gz.zero_()
+    ops.prep_operand(ops.make_src(ops.View(nhwc(x), 0)), cin, xz, 4)
+    ops.prep_operand(ops.make_src(ops.View(nhwc(g), 0)), cout, gz, 2)
+    dw = torch.zeros(cout, cin, k, k, device=DEV)
+    assert ops.conv2_wgrad(xz, 4, gz, 2, dw, N, H, W, cin, cout, k)
+    torch.cuda.synchronize()
+    err = (dw.double() - ref).abs().max().item()
+    assert err <= 6e-5 * ref.abs().max().item(), (err, ref.abs().max().item())
+    # accumulation: a second call doubles the result
+    assert ops.conv2_wgrad(xz, 4, gz, 2, dw, N, H, W, cin, cout, k)
+    torch.cuda.synchronize()
+    assert (dw.double() - 2 * ref).abs().max().item() <= 1.2e-4 * ref.abs().max().item()
+
+
+def test_conv2_wgrad_reports_unsupported_shapes():
+    from consistent_depth_b200 import ops
+    N, H, W = 1, 8, 8
+    xz = ops.z_alloc(N, 48, H, W, DEV); gz = ops.z_alloc(N, 16, H, W, DEV)
+    dw = torch.zeros(16, 48, 3, 3, device=DEV)
+    assert ops.conv2_wgrad(xz, 0, gz, 0, dw, N, H, W, 48, 16, 3) is False        # 48 input channels: 6 chunks do not tile M = 128

@@ -38,9 +38,9 @@ def fake_lib(monkeypatch):
 
 def _wgrad_targets(rec):
     out = collections.Counter()
-    for name in ("cvd_conv_wgrad", "cvd_conv_wgrad_grouped"):
+    for name, idx in (("cvd_conv_wgrad", 2), ("cvd_conv_wgrad_grouped", 2), ("cvd_conv2_wgrad", 6)):
         for a in rec.args[name]:
-            out[a[2].value] += 1
+            out[a[idx].value] += 1
     return out
 
 
@@ -138,7 +138,8 @@ def test_mannequin_challenge_plan(fake_lib):
     assert fake_lib.calls["cvd_bn_stats"] == 0                 # statistics come from the conv epilogues
     n_prep_fwd = fake_lib.calls["cvd_prep_operand"]
     e.backward(torch.rand(2, 32, 48))
-    assert fake_lib.calls["cvd_conv_wgrad"] == fwd_convs
+    # weight gradients: every inception conv on the operand planes (cvd_conv2_wgrad), conv1 / pred on the fp32 views
+    assert fake_lib.calls["cvd_conv2_wgrad"] == 4 * n_inc and fake_lib.calls["cvd_conv_wgrad"] == 2
     # backward: one gradient-operand preparation per BatchNorm group (k x k outputs, 1x1 outputs), dgrads on the new kernel
     # (4 per inception) except the pred layer's; conv1 has no input gradient
     assert fake_lib.calls["cvd_prep_operand"] - n_prep_fwd == 2 * n_inc

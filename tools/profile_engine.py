@@ -64,6 +64,9 @@ def main():
                 if name in ("cvd_conv_fwd", "cvd_conv_fwd_bn", "cvd_conv_wgrad", "cvd_conv_wgrad_grouped"):
                     ints = [x for x in a if type(x) is int]          # N, H, W, cin, cout, k, ... (pointers are ctypes objects)
                     key = f"{name} {ints[:6]}"
+                elif name == "cvd_conv2_fwd":                        # zc8, zc8_off, N, H, W, cin, cout, k, flags
+                    ints = [x for x in a if type(x) is int]
+                    key = f"{name} {ints[2:8]}"
                 recs.append((key, name, e0, e1))
                 return rc
             return timed
