@@ -184,6 +184,10 @@ class McEngine:
         # bf16x3 parity mode only.
         self.v2 = os.environ.get("CVD_CONV2", "1") == "1" and precision == 3
         self.v2_wgrad = self.v2 and os.environ.get("CVD_WGRAD2", "1") == "1"       # weight gradients on the same operand planes
+        # Per-layer dispatch (tools/conv2_microbench.py, B200): the kx-fused kernel wins where the GEMM N of the per-tap
+        # kernel is small (<= 32 output channels: 2.2x on 64->16 11x11) and for 1x1 convs; with N >= 64 the per-tap kernel
+        # already runs the tensor pipe at ~76 % and has no idle window lanes, so those k x k convs stay on it.
+        self.v2_nmax = int(os.environ.get("CVD_CONV2_NMAX", "32"))
         self.side_streams = []
         self.pmap, self.grad_flat = params.pmap, params.grad_flat
         self._p, self._g, self._rb = params._p, params._g, params._rb
@@ -340,7 +344,7 @@ class McEngine:
             mid.zsrc = (zmid, (aoff - o0) // 8)                # where this conv's input lives in the prepared planes
             self.fwd = []
             ko = boff - (o0 + A)
-            if v2:
+            if v2 and Bs[i] <= self.v2_nmax:
                 self._conv2(zmid, (aoff - o0) // 8, f"{prefix}.convs.{i + 1}.3.weight", f"{prefix}.convs.{i + 1}.3.bias",
                             _T(buf, off=boff), As[i], Bs[i], ks[i], h, w, bn=(one, rmk[ko:ko + Bs[i]], rvk[ko:ko + Bs[i]], None, None, i))
             else:
@@ -466,7 +470,7 @@ class McEngine:
                         self.bwd.append(lambda gs=gs, xs=xs, dW=dW, ci=As[i], co=Bs[i], k=ks[i], h=h, w=w:
                                         ops.conv_wgrad(gs, xs, dW, N, h, w, ci, co, k, prec))
                     d = ops.make_dst(mids[i].dview())
-                    if v2:
+                    if v2 and As[i] <= self.v2_nmax:
                         pkt = torch.empty(ops.conv2_packed_bytes(Bs[i], As[i], ks[i]), dtype=torch.uint8, device=self.dev)
                         self.pack2_bwd.append((Wt, pkt, True))
                         self.bwd.append(lambda gzk=gzk, zo=boffs[i] // 8, pkt=pkt, d=d, ci=Bs[i], co=As[i], k=ks[i], h=h, w=w:

@@ -127,24 +127,28 @@ def test_mannequin_challenge_plan(fake_lib):
     assert e.forward(torch.rand(2, 3, 32, 48)).shape == (2, 32, 48)
     n_inc = sum(1 for k in mc_arch.state_dict_shapes() if k.endswith(".convs.0.0.weight"))
     assert n_inc == 22
-    # conv1 and the pred layer (3 / 1 channels) stay on the first-generation kernel; every inception conv (fused 1x1 + three
-    # k x k) runs the TMA-fed kx-fused kernel on operands prepared once: the block input (unless another block already
-    # prepared the same tensor) and the 1x1 outputs a1|a2|a3
-    assert fake_lib.calls["cvd_conv_fwd"] + fake_lib.calls["cvd_conv_fwd_bn"] == 2
-    assert fake_lib.calls["cvd_conv2_fwd"] == 4 * n_inc
+    # Dispatch: conv1 and the pred layer (3 / 1 channels) and the k x k convs with >= 64 GEMM-N channels stay on the
+    # first-generation per-tap kernel; the fused 1x1 convs and the k x k convs with <= 32 output channels run the TMA-fed
+    # kx-fused kernel.  Operands are prepared once: the block input (unless another block already prepared the same
+    # tensor) and the 1x1 outputs a1|a2|a3.
+    kk = [s_ for k_, s_ in mc_arch.state_dict_shapes().items() if ".convs." in k_ and k_.endswith(".3.weight")]
+    assert len(kk) == 3 * n_inc
+    fwd_v2 = sum(1 for s_ in kk if s_[0] <= 32)                # (Cout, Cin, k, k): forward GEMM N = Cout
+    dgrad_v2 = sum(1 for s_ in kk if s_[1] <= 32)              # dgrad GEMM N = Cin
+    assert 0 < fwd_v2 < len(kk) and 0 < dgrad_v2 < len(kk)
+    assert fake_lib.calls["cvd_conv_fwd"] + fake_lib.calls["cvd_conv_fwd_bn"] == 2 + len(kk) - fwd_v2
+    assert fake_lib.calls["cvd_conv2_fwd"] == n_inc + fwd_v2
     assert n_inc < fake_lib.calls["cvd_prep_operand"] <= 2 * n_inc
     assert fake_lib.calls["cvd_conv2_pack_batch"] == 1
-    fwd_convs = 2 + 4 * n_inc
     assert fake_lib.calls["cvd_bn_stats"] == 0                 # statistics come from the conv epilogues
-    n_prep_fwd = fake_lib.calls["cvd_prep_operand"]
+    n_prep_fwd, n_v1_fwd = fake_lib.calls["cvd_prep_operand"], fake_lib.calls["cvd_conv_fwd"] + fake_lib.calls["cvd_conv_fwd_bn"]
     e.backward(torch.rand(2, 32, 48))
     # weight gradients: every inception conv on the operand planes (cvd_conv2_wgrad), conv1 / pred on the fp32 views
     assert fake_lib.calls["cvd_conv2_wgrad"] == 4 * n_inc and fake_lib.calls["cvd_conv_wgrad"] == 2
-    # backward: one gradient-operand preparation per BatchNorm group (k x k outputs, 1x1 outputs), dgrads on the new kernel
-    # (4 per inception) except the pred layer's; conv1 has no input gradient
+    # backward: one gradient-operand preparation per BatchNorm group (k x k outputs, 1x1 outputs); conv1 has no input gradient
     assert fake_lib.calls["cvd_prep_operand"] - n_prep_fwd == 2 * n_inc
-    assert fake_lib.calls["cvd_conv2_fwd"] == 8 * n_inc
-    assert fake_lib.calls["cvd_conv_fwd"] + fake_lib.calls["cvd_conv_fwd_bn"] == 3
+    assert fake_lib.calls["cvd_conv2_fwd"] == n_inc + fwd_v2 + n_inc + dgrad_v2
+    assert fake_lib.calls["cvd_conv_fwd"] + fake_lib.calls["cvd_conv_fwd_bn"] == n_v1_fwd + 1 + len(kk) - dgrad_v2
     targets = _wgrad_targets(fake_lib)
     for k, (off, shape) in P.pmap.items():
         if len(shape) != 4:

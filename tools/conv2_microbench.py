@@ -56,6 +56,39 @@ def bench_shape(cin, cout, k, H, W, N, reps, do_v1=True):
     return out
 
 
+def bench_wgrad(cin, cout, k, H, W, N, reps):
+    dev = "cuda:0"
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.rand(N, H, W, cin, device=dev, generator=g) - 0.5
+    gy = torch.rand(N, H, W, cout, device=dev, generator=g) - 0.5
+    xr = torch.rand(N, H, W, cout, device=dev, generator=g) - 0.5
+    sa = torch.rand(cin, device=dev) + 0.5; sb = torch.rand(cin, device=dev) - 0.5
+    ga = torch.rand(cout, device=dev) + 0.5; gb = torch.rand(cout, device=dev) - 0.5; bw = torch.rand(cout, 4, device=dev)
+    dw = torch.zeros(cout, cin, k, k, device=dev)
+    gsrc = ops.make_src(ops.View(xr), ga, gb, True, dy=ops.View(gy), bw=bw)
+    xsrc = ops.make_src(ops.View(x), sa, sb, True)
+    out = {"v1_ms": time_it(lambda: ops.conv_wgrad(gsrc, xsrc, dw, N, H, W, cin, cout, k, 3), reps)}
+    xz, gz = ops.z_alloc(N, cin, H, W, dev), ops.z_alloc(N, cout, H, W, dev)
+    ops.prep_operand(xsrc, cin, xz); ops.prep_operand(gsrc, cout, gz)
+    ok = ops.conv2_wgrad(xz, 0, gz, 0, dw, N, H, W, cin, cout, k)
+    out["v2_ms"] = time_it(lambda: ops.conv2_wgrad(xz, 0, gz, 0, dw, N, H, W, cin, cout, k), reps) if ok else None
+    return out
+
+
+def main_wgrad(a):
+    rows, tot = [], {"v1": 0.0, "v2": 0.0}
+    for (ci, co, k, H, W, cnt) in FWD:
+        r = bench_wgrad(ci, co, k, H, W, a.N, a.reps)
+        gf = 2.0 * k * k * ci * co * a.N * H * W
+        v2 = r["v2_ms"] if r["v2_ms"] is not None else r["v1_ms"]
+        rows.append({"kind": "wgrad", "cin": ci, "cout": co, "k": k, "H": H, "W": W, "count": cnt, **r})
+        tot["v1"] += cnt * r["v1_ms"]; tot["v2"] += cnt * v2
+        print(f"wgrad {ci:3d}->{co:3d} k{k:2d} {H:3d}x{W:3d} x{cnt}: v1 {r['v1_ms']:.3f} ms ({gf / r['v1_ms'] / 1e9:.0f} TF)  "
+              f"v2 {v2:.3f} ms ({gf / v2 / 1e9:.0f} TF){'' if r['v2_ms'] is not None else ' [unsupported: v1]'}", flush=True)
+    print("wgrad per-step totals (count-weighted):", tot)
+    json.dump({"N": a.N, "rows": rows, "totals_ms": tot}, open(a.out, "w"), indent=1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/conv2_mb.json")
@@ -63,7 +96,11 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--only-big", action="store_true")
+    ap.add_argument("--wgrad", action="store_true", help="weight-gradient kernels (conv_wgrad vs conv2_wgrad) instead")
     a = ap.parse_args()
+    if a.wgrad:
+        os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
+        return main_wgrad(a)
     shapes = []
     for (ci, co, k, H, W, cnt) in FWD:
         shapes.append(("fwd", ci, co, k, H, W, cnt))
