@@ -48,6 +48,7 @@ struct C2Args {
   int plane_bytes, a_stage_bytes, NA;
   int b_tile_bytes, NB, b_resident, b_tiles;   // b_tiles = weight tiles per CTA tile (nkb * k * ng)
   int nbuf, tmem_cols;
+  int SBW;                                     // columns of the store staging block (16..64)
   int flags;
   bnepi::Stats st;                             // st.scratch == nullptr: no fused BatchNorm statistics
 };
@@ -70,7 +71,9 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
   uint8_t* a_ring = smem;                                                      // NA x (a_stage_bytes + kAPad)
   uint8_t* b_ring = a_ring + (size_t)p.NA * (p.a_stage_bytes + kAPad);          // NB x b_tile_bytes
   float* obuf = reinterpret_cast<float*>(b_ring + (size_t)p.NB * p.b_tile_bytes);   // [128][kOPitch]
-  float* sstat = obuf + 128 * kOPitch;                                         // [4][2][Cp]
+  float* sbuf = obuf + 128 * kOPitch;                                          // [128][SBW + 4] store staging block
+  long long* rowoff = reinterpret_cast<long long*>(sbuf + 128 * (p.SBW + 4)); // [128] element offset of each row's pixel (-1: no store)
+  float* sstat = reinterpret_cast<float*>(rowoff + 128);                       // [4][2][Cp]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 8 * p.Cp);
   uint64_t* a_full = bars;                      // [kMaxA]
   uint64_t* a_empty = a_full + kMaxA;           // [kMaxA]
@@ -188,11 +191,18 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
     }
   } else {
     // ============================ epilogue ============================
+    // tcgen05.ld -> (shifted sum through obuf) -> bias / BN statistics / exp in registers -> staging block sbuf[128][SBW]
+    // -> cooperative copy-out: consecutive threads write consecutive 16 B of one pixel's channel run, so a warp store is a
+    // few full 32-B-sector runs instead of 32 scattered half sectors (the per-thread row stores were the bound of the
+    // 1x1 convolutions: 52 store instructions x 32 sectors per M-tile at N = 208).
     const int q = warp & 3;                          // TMEM lane quarter of this warp
     const int s = q * 32 + lane;                     // window slot of the M-tile held by this thread
+    const int et = threadIdx.x - 96;                 // 0..127
     const int r = s / p.WS, sx = s - r * p.WS;
     const bool accum = (p.flags & 1) != 0, do_exp = (p.flags & 2) != 0;
     float* orow = obuf + s * kOPitch;
+    const int spitch = p.SBW + 4;
+    float* srow = sbuf + s * spitch;
     int ti = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
       int t = tile;
@@ -205,56 +215,68 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
       for (int mt = 0; mt < p.MT; ++mt) {
         const int yy = oy + mt * p.R + r, xx = ox + sx;
         const bool inside = sx < p.VW && yy < p.Hv && xx < p.Wv;
-        float* yp = p.y + ((size_t)n * p.HW + (inside ? (size_t)yy * p.Wv + xx : 0)) * p.y_ct;
+        rowoff[s] = inside ? ((long long)n * p.HW + (long long)yy * p.Wv + xx) * p.y_ct : -1ll;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.MT + mt) * p.Ncols);
-        for (int c16 = 0; c16 < p.Cp; c16 += 16) {
-          float v[16];
-          tc::tmem_ld16(taddr + (uint32_t)c16, v);                          // j = 0
-          if (p.G > 1) {
-            // out[x] = sum_j D[x + j][j]: slot s adds its j-th block into row s - j (rows are distinct per j)
+        for (int c0 = 0; c0 < p.Cp; c0 += p.SBW) {
+          const int ncb = min(p.SBW, p.Cp - c0);       // columns of this staging block (multiple of 16)
+          for (int c16 = c0; c16 < c0 + ncb; c16 += 16) {
+            float v[16];
+            tc::tmem_ld16(taddr + (uint32_t)c16, v);                          // j = 0
+            if (p.G > 1) {
+              // out[x] = sum_j D[x + j][j]: slot s adds its j-th block into row s - j (rows are distinct per j)
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(orow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int j = 1; j < p.G; ++j) {
-              tc::tmem_ld16(taddr + (uint32_t)(j * p.Cp + c16), v);
-              if (sx >= j) {
-                float* tr = orow - j * kOPitch;
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                  float4 o = *reinterpret_cast<const float4*>(tr + i);
-                  o.x += v[i]; o.y += v[i + 1]; o.z += v[i + 2]; o.w += v[i + 3];
-                  *reinterpret_cast<float4*>(tr + i) = o;
-                }
-              }
+              for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(orow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
               asm volatile("bar.sync 1, 128;" ::: "memory");
+              for (int j = 1; j < p.G; ++j) {
+                tc::tmem_ld16(taddr + (uint32_t)(j * p.Cp + c16), v);
+                if (sx >= j) {
+                  float* tr = orow - j * kOPitch;
+#pragma unroll
+                  for (int i = 0; i < 16; i += 4) {
+                    float4 o = *reinterpret_cast<const float4*>(tr + i);
+                    o.x += v[i]; o.y += v[i + 1]; o.z += v[i + 2]; o.w += v[i + 3];
+                    *reinterpret_cast<float4*>(tr + i) = o;
+                  }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+              }
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 o = *reinterpret_cast<const float4*>(orow + i);
+                v[i] = o.x; v[i + 1] = o.y; v[i + 2] = o.z; v[i + 3] = o.w;
+              }
+            }
+            if (p.bias) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) if (c16 + i < p.cout_valid) v[i] += __ldg(p.bias + c16 + i);
+            }
+            if (p.st.scratch) bnepi::accumulate16(v, inside, lane, sstat + (size_t)q * 2 * p.Cp, p.Cp, c16);
+            if (do_exp) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = expf(v[i]);
             }
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 o = *reinterpret_cast<const float4*>(orow + i);
-              v[i] = o.x; v[i + 1] = o.y; v[i + 2] = o.z; v[i + 3] = o.w;
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(srow + (c16 - c0) + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          // copy-out of the 128 x ncb block
+          const int f4r = ncb >> 2;
+          for (int idx = et; idx < 128 * f4r; idx += 128) {
+            const int row = idx / f4r, f = idx - row * f4r;
+            const long long ro = rowoff[row];
+            const int c = c0 + 4 * f;
+            if (ro < 0 || c >= p.cout_valid) continue;
+            float4 o = *reinterpret_cast<const float4*>(sbuf + row * spitch + 4 * f);
+            float* dst = p.y + ro + view_phys(c, p.y_c0, p.y_n0, p.y_gap);
+            if (c + 4 <= p.cout_valid) {
+              if (accum) { const float4 old = *reinterpret_cast<const float4*>(dst); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+              *reinterpret_cast<float4*>(dst) = o;
+            } else {
+              const float ov[4] = {o.x, o.y, o.z, o.w};
+              for (int i = 0; i < p.cout_valid - c; ++i) dst[i] = accum ? dst[i] + ov[i] : ov[i];
             }
           }
-          if (p.bias) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) if (c16 + i < p.cout_valid) v[i] += __ldg(p.bias + c16 + i);
-          }
-          if (p.st.scratch) bnepi::accumulate16(v, inside, lane, sstat + (size_t)q * 2 * p.Cp, p.Cp, c16);
-          if (!inside || c16 >= p.cout_valid) continue;
-          if (do_exp) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = expf(v[i]);
-          }
-          float* dst = yp + view_phys(c16, p.y_c0, p.y_n0, p.y_gap);
-          if (c16 + 16 <= p.cout_valid) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-              if (accum) { const float4 old = *reinterpret_cast<const float4*>(dst + i); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-              *reinterpret_cast<float4*>(dst + i) = o;
-            }
-          } else {
-            for (int i = 0; i < p.cout_valid - c16; ++i) dst[i] = accum ? dst[i] + v[i] : v[i];
-          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
         }
       }
       tc::tc_fence_before();
@@ -418,13 +440,15 @@ extern "C" int cvd_conv2_fwd(const void* z, int zc8, int zc8_off, const void* pa
   // grid fill: prefer at least one tile per SM
   const int tiles_x = (p.Wv + p.VW - 1) / p.VW;
   while (mt > 1 && (long long)N * tiles_x * ((p.Hv + mt * p.R - 1) / (mt * p.R)) < cvd_num_sms()) --mt;
+  p.SBW = p.Cp < 64 ? p.Cp : 64;
+  const int sb_bytes = 128 * (p.SBW + 4) * 4 + 128 * 8;
   const int smem_budget = 224 * 1024;
   bool found = false;
   for (; mt >= 1 && !found; --mt) {
     p.MT = mt; p.TR = mt * p.R; p.WR = p.TR + k - 1;
     p.plane_bytes = p.WR * p.WS * 16; p.a_stage_bytes = 4 * p.plane_bytes;
     p.b_tile_bytes = 64 * p.Ncols; p.b_tiles = p.nkb * k * p.ng;
-    const size_t fixed = 128 * kOPitch * 4 + 8 * p.Cp * 4 + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64 + 1024;
+    const size_t fixed = 128 * kOPitch * 4 + sb_bytes + 8 * p.Cp * 4 + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64 + 1024;
     // weights resident in shared memory (1x1 convolutions): loaded once per CTA
     const size_t res_bytes = (size_t)p.b_tiles * p.b_tile_bytes;
     const bool allow_res = !(getenv("CVD2_NO_RESIDENT") && getenv("CVD2_NO_RESIDENT")[0] == '1');
@@ -465,7 +489,7 @@ extern "C" int cvd_conv2_fwd(const void* z, int zc8, int zc8_off, const void* pa
   CVD_CHECK_ARG(cr == CUDA_SUCCESS, "cvd_conv2_fwd: cuTensorMapEncodeTiled failed (%d) [Wv=%d Hv=%d zc8=%d N=%d WS=%d WR=%d]",
                 (int)cr, p.Wv, p.Hv, zc8, N, p.WS, p.WR);
 
-  const size_t smem = (size_t)p.NA * (p.a_stage_bytes + kAPad) + (size_t)p.NB * p.b_tile_bytes + 128 * kOPitch * 4 + 8 * p.Cp * 4 +
+  const size_t smem = (size_t)p.NA * (p.a_stage_bytes + kAPad) + (size_t)p.NB * p.b_tile_bytes + 128 * kOPitch * 4 + sb_bytes + 8 * p.Cp * 4 +
                       (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64;
   const long long grid = p.ntiles < cvd_num_sms() ? p.ntiles : cvd_num_sms();
   static bool cfg = false;

@@ -9,6 +9,7 @@
 // Every kernel streams its tensors exactly once with 128-bit accesses; per-channel
 // reductions go block-local in fp32, cross-block in fp64 atomics (few thousand per layer).
 #include "cvd_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -438,7 +439,8 @@ extern "C" int cvd_bn_bwd_reduce(const float* x, int x_ctotal, int x_coff,
                 "cvd_bn_bwd_reduce: bad channels");
   const int lanes = 256 / (C >> 2);
   long long blocks = (npix + lanes * 16 - 1) / ((long long)lanes * 16);
-  const long long cap = (long long)cvd_num_sms() * 3;
+  static const int bpsm = getenv("CVD_BNBWD_BLOCKS") ? atoi(getenv("CVD_BNBWD_BLOCKS")) : 3;
+  const long long cap = (long long)cvd_num_sms() * (bpsm > 0 ? bpsm : 3);
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   bn_bwd_reduce_kernel<<<(unsigned)blocks, 256, 2 * C * sizeof(double), (cudaStream_t)stream>>>(

@@ -461,7 +461,9 @@ class McEngine:
                     Wt = self._p(f"{prefix}.convs.{i + 1}.3.weight")
                     gs, xs = outs[i].bnbwd_src(), mids[i].src()
                     dW = self._g(f"{prefix}.convs.{i + 1}.3.weight")
-                    if v2 and self.v2_wgrad:
+                    # wgrad dispatch (tools/conv2_microbench.py --wgrad, B200): the TMA-fed kernel wins for the wide filters
+                    # (2.3x on 64->16 11x11) and few channels; for 3x3 / 5x5 it is bound by L2->SM window traffic
+                    if v2 and self.v2_wgrad and ((ks[i] >= 7 and As[i] >= Bs[i]) or (As[i] <= 32 and Bs[i] <= 16)):
                         zmid, xo = mids[i].zsrc
                         self.bwd.append(lambda zmid=zmid, xo=xo, gzk=gzk, go=boffs[i] // 8, gs=gs, xs=xs, dW=dW, ci=As[i], co=Bs[i], k=ks[i], h=h, w=w:
                                         ops.conv2_wgrad(zmid, xo, gzk, go, dW, N, h, w, ci, co, k) or
