@@ -33,7 +33,8 @@
 namespace {
 
 constexpr int kThreads = 32 * 7;
-constexpr int kMaxA = 4, kMaxB = 32;
+constexpr int kMaxA = 12, kMaxB = 32;        // A stages: 1x1 convs need ~80 KB of activation loads in flight per SM to cover
+                                               // the HBM latency (8 KB stages), k x k windows are 40-70 KB each (2 stages)
 constexpr int kAPad = 256;                     // zeroed bytes behind every A stage: a zero-weight (padded) tap of the last
                                                // window row reads up to G slots past the stage and must not meet NaN / Inf garbage
 constexpr int kOPitch = 20;                    // floats per obuf row (16 + 4: conflict-free float4 access)
@@ -48,7 +49,6 @@ struct C2Args {
   int plane_bytes, a_stage_bytes, NA;
   int b_tile_bytes, NB, b_resident, b_tiles;   // b_tiles = weight tiles per CTA tile (nkb * k * ng)
   int nbuf, tmem_cols;
-  int SBW;                                     // columns of the store staging block (16..64)
   int flags;
   bnepi::Stats st;                             // st.scratch == nullptr: no fused BatchNorm statistics
 };
@@ -71,10 +71,9 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
   uint8_t* a_ring = smem;                                                      // NA x (a_stage_bytes + kAPad)
   uint8_t* b_ring = a_ring + (size_t)p.NA * (p.a_stage_bytes + kAPad);          // NB x b_tile_bytes
   float* obuf = reinterpret_cast<float*>(b_ring + (size_t)p.NB * p.b_tile_bytes);   // [128][kOPitch]
-  float* sbuf = obuf + 128 * kOPitch;                                          // [128][SBW + 4] store staging block
-  long long* rowoff = reinterpret_cast<long long*>(sbuf + 128 * (p.SBW + 4)); // [128] element offset of each row's pixel (-1: no store)
-  float* sstat = reinterpret_cast<float*>(rowoff + 128);                       // [4][2][Cp]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 8 * p.Cp);
+  float* sstat = obuf + 128 * kOPitch;                                         // [4][2][Cp]
+  float* sbias = sstat + 8 * p.Cp;                                             // [Cp] (zeros when the conv has no bias)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + p.Cp);
   uint64_t* a_full = bars;                      // [kMaxA]
   uint64_t* a_empty = a_full + kMaxA;           // [kMaxA]
   uint64_t* b_full = a_empty + kMaxA;           // [kMaxB]
@@ -85,6 +84,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.st.scratch) for (int i = threadIdx.x; i < 8 * p.Cp; i += kThreads) sstat[i] = 0.f;
+  for (int i = threadIdx.x; i < p.Cp; i += kThreads) sbias[i] = (p.bias && i < p.cout_valid) ? __ldg(p.bias + i) : 0.f;
   for (int i = threadIdx.x; i < p.NA * (kAPad / 16); i += kThreads)
     *reinterpret_cast<uint4*>(a_ring + (size_t)(i / (kAPad / 16)) * (p.a_stage_bytes + kAPad) + p.a_stage_bytes + (i % (kAPad / 16)) * 16) = make_uint4(0u, 0u, 0u, 0u);
   tc::fence_proxy_async_smem();
@@ -191,18 +191,11 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
     }
   } else {
     // ============================ epilogue ============================
-    // tcgen05.ld -> (shifted sum through obuf) -> bias / BN statistics / exp in registers -> staging block sbuf[128][SBW]
-    // -> cooperative copy-out: consecutive threads write consecutive 16 B of one pixel's channel run, so a warp store is a
-    // few full 32-B-sector runs instead of 32 scattered half sectors (the per-thread row stores were the bound of the
-    // 1x1 convolutions: 52 store instructions x 32 sectors per M-tile at N = 208).
     const int q = warp & 3;                          // TMEM lane quarter of this warp
     const int s = q * 32 + lane;                     // window slot of the M-tile held by this thread
-    const int et = threadIdx.x - 96;                 // 0..127
     const int r = s / p.WS, sx = s - r * p.WS;
     const bool accum = (p.flags & 1) != 0, do_exp = (p.flags & 2) != 0;
     float* orow = obuf + s * kOPitch;
-    const int spitch = p.SBW + 4;
-    float* srow = sbuf + s * spitch;
     int ti = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
       int t = tile;
@@ -215,68 +208,59 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
       for (int mt = 0; mt < p.MT; ++mt) {
         const int yy = oy + mt * p.R + r, xx = ox + sx;
         const bool inside = sx < p.VW && yy < p.Hv && xx < p.Wv;
-        rowoff[s] = inside ? ((long long)n * p.HW + (long long)yy * p.Wv + xx) * p.y_ct : -1ll;
+        float* yp = p.y + ((size_t)n * p.HW + (inside ? (size_t)yy * p.Wv + xx : 0)) * p.y_ct;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.MT + mt) * p.Ncols);
-        for (int c0 = 0; c0 < p.Cp; c0 += p.SBW) {
-          const int ncb = min(p.SBW, p.Cp - c0);       // columns of this staging block (multiple of 16)
-          for (int c16 = c0; c16 < c0 + ncb; c16 += 16) {
-            float v[16];
-            tc::tmem_ld16(taddr + (uint32_t)c16, v);                          // j = 0
-            if (p.G > 1) {
-              // out[x] = sum_j D[x + j][j]: slot s adds its j-th block into row s - j (rows are distinct per j)
+        for (int c16 = 0; c16 < p.Cp; c16 += 16) {
+          float v[16];
+          tc::tmem_ld16(taddr + (uint32_t)c16, v);                          // j = 0
+          if (p.G > 1) {
+            // out[x] = sum_j D[x + j][j]: slot s adds its j-th block into row s - j (rows are distinct per j)
 #pragma unroll
-              for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(orow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-              asm volatile("bar.sync 1, 128;" ::: "memory");
-              for (int j = 1; j < p.G; ++j) {
-                tc::tmem_ld16(taddr + (uint32_t)(j * p.Cp + c16), v);
-                if (sx >= j) {
-                  float* tr = orow - j * kOPitch;
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(orow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int j = 1; j < p.G; ++j) {
+              tc::tmem_ld16(taddr + (uint32_t)(j * p.Cp + c16), v);
+              if (sx >= j) {
+                float* tr = orow - j * kOPitch;
 #pragma unroll
-                  for (int i = 0; i < 16; i += 4) {
-                    float4 o = *reinterpret_cast<const float4*>(tr + i);
-                    o.x += v[i]; o.y += v[i + 1]; o.z += v[i + 2]; o.w += v[i + 3];
-                    *reinterpret_cast<float4*>(tr + i) = o;
-                  }
+                for (int i = 0; i < 16; i += 4) {
+                  float4 o = *reinterpret_cast<const float4*>(tr + i);
+                  o.x += v[i]; o.y += v[i + 1]; o.z += v[i + 2]; o.w += v[i + 3];
+                  *reinterpret_cast<float4*>(tr + i) = o;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
               }
-#pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                const float4 o = *reinterpret_cast<const float4*>(orow + i);
-                v[i] = o.x; v[i + 1] = o.y; v[i + 2] = o.z; v[i + 3] = o.w;
-              }
-            }
-            if (p.bias) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) if (c16 + i < p.cout_valid) v[i] += __ldg(p.bias + c16 + i);
-            }
-            if (p.st.scratch) bnepi::accumulate16(v, inside, lane, sstat + (size_t)q * 2 * p.Cp, p.Cp, c16);
-            if (do_exp) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = expf(v[i]);
+              asm volatile("bar.sync 1, 128;" ::: "memory");
             }
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(srow + (c16 - c0) + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          // copy-out of the 128 x ncb block
-          const int f4r = ncb >> 2;
-          for (int idx = et; idx < 128 * f4r; idx += 128) {
-            const int row = idx / f4r, f = idx - row * f4r;
-            const long long ro = rowoff[row];
-            const int c = c0 + 4 * f;
-            if (ro < 0 || c >= p.cout_valid) continue;
-            float4 o = *reinterpret_cast<const float4*>(sbuf + row * spitch + 4 * f);
-            float* dst = p.y + ro + view_phys(c, p.y_c0, p.y_n0, p.y_gap);
-            if (c + 4 <= p.cout_valid) {
-              if (accum) { const float4 old = *reinterpret_cast<const float4*>(dst); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-              *reinterpret_cast<float4*>(dst) = o;
-            } else {
-              const float ov[4] = {o.x, o.y, o.z, o.w};
-              for (int i = 0; i < p.cout_valid - c; ++i) dst[i] = accum ? dst[i] + ov[i] : ov[i];
+            for (int i = 0; i < 16; i += 4) {
+              const float4 o = *reinterpret_cast<const float4*>(orow + i);
+              v[i] = o.x; v[i + 1] = o.y; v[i + 2] = o.z; v[i + 3] = o.w;
             }
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 bq = *reinterpret_cast<const float4*>(sbias + c16 + i);     // broadcast read
+              v[i] += bq.x; v[i + 1] += bq.y; v[i + 2] += bq.z; v[i + 3] += bq.w;
+            }
+          }
+          if (p.st.scratch) bnepi::accumulate16(v, inside, lane, sstat + (size_t)q * 2 * p.Cp, p.Cp, c16);
+          if (!inside || c16 >= p.cout_valid) continue;
+          if (do_exp) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = expf(v[i]);
+          }
+          float* dst = yp + view_phys(c16, p.y_c0, p.y_n0, p.y_gap);
+          if (c16 + 16 <= p.cout_valid) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              if (accum) { const float4 old = *reinterpret_cast<const float4*>(dst + i); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+              *reinterpret_cast<float4*>(dst + i) = o;
+            }
+          } else {
+            for (int i = 0; i < p.cout_valid - c16; ++i) dst[i] = accum ? dst[i] + v[i] : v[i];
+          }
         }
       }
       tc::tc_fence_before();
@@ -440,15 +424,13 @@ extern "C" int cvd_conv2_fwd(const void* z, int zc8, int zc8_off, const void* pa
   // grid fill: prefer at least one tile per SM
   const int tiles_x = (p.Wv + p.VW - 1) / p.VW;
   while (mt > 1 && (long long)N * tiles_x * ((p.Hv + mt * p.R - 1) / (mt * p.R)) < cvd_num_sms()) --mt;
-  p.SBW = p.Cp < 64 ? p.Cp : 64;
-  const int sb_bytes = 128 * (p.SBW + 4) * 4 + 128 * 8;
   const int smem_budget = 224 * 1024;
   bool found = false;
   for (; mt >= 1 && !found; --mt) {
     p.MT = mt; p.TR = mt * p.R; p.WR = p.TR + k - 1;
     p.plane_bytes = p.WR * p.WS * 16; p.a_stage_bytes = 4 * p.plane_bytes;
     p.b_tile_bytes = 64 * p.Ncols; p.b_tiles = p.nkb * k * p.ng;
-    const size_t fixed = 128 * kOPitch * 4 + sb_bytes + 8 * p.Cp * 4 + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64 + 1024;
+    const size_t fixed = 128 * kOPitch * 4 + 9 * p.Cp * 4 + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64 + 1024;
     // weights resident in shared memory (1x1 convolutions): loaded once per CTA
     const size_t res_bytes = (size_t)p.b_tiles * p.b_tile_bytes;
     const bool allow_res = !(getenv("CVD2_NO_RESIDENT") && getenv("CVD2_NO_RESIDENT")[0] == '1');
@@ -458,7 +440,11 @@ extern "C" int cvd_conv2_fwd(const void* z, int zc8, int zc8_off, const void* pa
       p.NA = na > kMaxA ? kMaxA : na;
       found = true; break;
     }
-    for (int na = 2; na >= 1 && !found; --na) {
+    // streamed weights: enough activation stages for ~96 KB of loads in flight (at least two), then the weight ring
+    int na_want = (96 * 1024 + p.a_stage_bytes - 1) / p.a_stage_bytes;
+    if (na_want < 2) na_want = 2;
+    if (na_want > kMaxA) na_want = kMaxA;
+    for (int na = na_want; na >= 1 && !found; --na) {
       const long long left = (long long)smem_budget - (long long)fixed - (long long)na * (p.a_stage_bytes + kAPad);
       int nb = (int)(left / p.b_tile_bytes);
       if (nb > 6) nb = 6;
@@ -489,7 +475,7 @@ extern "C" int cvd_conv2_fwd(const void* z, int zc8, int zc8_off, const void* pa
   CVD_CHECK_ARG(cr == CUDA_SUCCESS, "cvd_conv2_fwd: cuTensorMapEncodeTiled failed (%d) [Wv=%d Hv=%d zc8=%d N=%d WS=%d WR=%d]",
                 (int)cr, p.Wv, p.Hv, zc8, N, p.WS, p.WR);
 
-  const size_t smem = (size_t)p.NA * (p.a_stage_bytes + kAPad) + (size_t)p.NB * p.b_tile_bytes + 128 * kOPitch * 4 + sb_bytes + 8 * p.Cp * 4 +
+  const size_t smem = (size_t)p.NA * (p.a_stage_bytes + kAPad) + (size_t)p.NB * p.b_tile_bytes + 128 * kOPitch * 4 + 9 * p.Cp * 4 +
                       (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64;
   const long long grid = p.ntiles < cvd_num_sms() ? p.ntiles : cvd_num_sms();
   static bool cfg = false;

@@ -143,8 +143,11 @@ def test_mannequin_challenge_plan(fake_lib):
     assert fake_lib.calls["cvd_bn_stats"] == 0                 # statistics come from the conv epilogues
     n_prep_fwd, n_v1_fwd = fake_lib.calls["cvd_prep_operand"], fake_lib.calls["cvd_conv_fwd"] + fake_lib.calls["cvd_conv_fwd_bn"]
     e.backward(torch.rand(2, 32, 48))
-    # weight gradients: every inception conv on the operand planes (cvd_conv2_wgrad), conv1 / pred on the fp32 views
-    assert fake_lib.calls["cvd_conv2_wgrad"] == 4 * n_inc and fake_lib.calls["cvd_conv_wgrad"] == 2
+    # weight gradients: the fused 1x1 convs and the wide / few-channel k x k convs on the operand planes (cvd_conv2_wgrad),
+    # the rest (and conv1 / pred) on the fp32 views
+    wg_v2 = sum(1 for s_ in kk if (s_[2] >= 7 and s_[1] >= s_[0]) or (s_[1] <= 32 and s_[0] <= 16))   # McEngine's wgrad dispatch rule
+    assert 0 < wg_v2 < len(kk)
+    assert fake_lib.calls["cvd_conv2_wgrad"] == n_inc + wg_v2 and fake_lib.calls["cvd_conv_wgrad"] == 2 + len(kk) - wg_v2
     # backward: one gradient-operand preparation per BatchNorm group (k x k outputs, 1x1 outputs); conv1 has no input gradient
     assert fake_lib.calls["cvd_prep_operand"] - n_prep_fwd == 2 * n_inc
     assert fake_lib.calls["cvd_conv2_fwd"] == n_inc + fwd_v2 + n_inc + dgrad_v2
