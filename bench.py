@@ -177,6 +177,105 @@ def gpu_reference(dev, steps=10, warmup=3):
     return out
 
 
+def parity_after_steps(dev, n_steps=5):
+    """Depth after n identical-order fine-tune steps: this repo's fused step vs the reference's GPU path (oracle port,
+    strict fp32 convolutions) from the SAME weights on the SAME batches.  Reported as a number (SURVEY 8(d) "parity
+    tolerances to state"): Adam's first updates are ~lr*sign(g), so trajectories of any two non-bit-identical
+    implementations separate; step-0 loss and the depth before any update are the tight comparisons."""
+    import numpy as np
+    from oracle import synth, hourglass_oracle as ho, consistency_oracle as co
+    from consistent_depth_b200.fine_tune_step import FineTuneStep
+    from consistent_depth_b200.monodepth.mannequin_challenge_model import MannequinChallengeModel
+    seed = 7
+    sd_np = ho.mc_init_state(seed)
+    sd_np["pred_layer.weight"] = sd_np["pred_layer.weight"] * 0.1
+    sd_np["pred_layer.bias"] = np.full((1,), np.log(2.0), np.float32)
+    batch = synth.make_pair_batch(1234, REF_PAIRS, H, W)
+    t = lambda a: torch.tensor(a, device=dev)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        P, buffers = ho.to_torch(sd_np, requires_grad=False)
+        P = {k: v.to(dev).requires_grad_(True) for k, v in P.items()}
+        buffers = {k: v.to(dev) for k, v in buffers.items()}
+        margs = (t(batch["extrinsics"]), t(batch["intrinsics"]), [t(f) for f in batch["flows"]], [t(m) for m in batch["masks"]])
+        images = t(batch["images"])
+        opt = torch.optim.Adam([P[k] for k in ho.trainable_keys()], 4e-4, betas=(0.9, 0.999))
+        ref_losses, ref_d0 = [], None
+        for it in range(n_steps):
+            depth = ho.estimate_depth(images, P, buffers)
+            if it == 0:
+                ref_d0 = depth.detach().clone()
+            opt.zero_grad()
+            loss, _ = co.consistency_loss(depth, *margs, 1.0, 0.1)
+            ref_losses.append(float(loss))
+            loss.backward(); opt.step()
+        with torch.no_grad():
+            ref_dn = ho.estimate_depth(images, P, buffers).clone()
+        del P, buffers, opt, depth, loss
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    model = MannequinChallengeModel(state_dict={k: torch.tensor(np.asarray(v)) for k, v in sd_np.items()})
+    step = FineTuneStep(model, BS, H, W, lr=4e-4, use_graph=False)
+    step.load_batch(images, margs[2], margs[3], margs[0], margs[1])
+    losses, d0 = [], None
+    for it in range(n_steps):
+        losses.append(float(step.step()))
+        if it == 0:
+            d0 = step.depth().clone()
+    step.engine.train_mode = True
+    dn = step.engine.forward(images.view(2 * BS, 3, H, W)).view(BS, 2, H, W).clone()
+    rel = lambda a, b: float(((a - b).abs() / b).mean())
+    out = {"steps": n_steps, "depth_rel_l1_before_any_update": rel(d0, ref_d0), "depth_rel_l1_after_steps": rel(dn, ref_dn),
+           "loss_rel_diff_per_step": [abs(a - b) / abs(b) for a, b in zip(losses, ref_losses)],
+           "against": "oracle port of the reference GPU path, strict fp32 convolutions, same weights / batches"}
+    del step, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def fine_tune_api(dev, precision, resident):
+    """Wall clock of the real entry point: DepthFineTuner.fine_tune() for ONE epoch of BASELINE config[1] (50 synthetic
+    frames written to disk in the reference's layout, 138 hierarchical2 pairs, BS4): loader (HBM-resident clip or the
+    reference's 4-worker file DataLoader), train-mode validation before and after, 35 fused steps, checkpoint."""
+    import contextlib, io, re, shutil, types
+    from consistent_depth_b200.depth_fine_tuning import DepthFineTuner
+    from consistent_depth_b200.monodepth.mannequin_challenge_model import default_init_state
+    from consistent_depth_b200.synthetic_dataset import write_synthetic_dataset
+    import math
+    root = tempfile.mkdtemp(prefix="cvd_bench_clip_")
+    try:
+        range_dir = os.path.join(root, "R0-50_hierarchical2_mc")
+        video = write_synthetic_dataset(root, range_dir, NFRAMES, H, W, device=dev, seed=1234 + 2)
+        n_pairs = len(video.pairs)
+        del video
+        params = types.SimpleNamespace(path=root, model_type="mc", batch_size=BS, learning_rate=0, optimizer="Adam", num_epochs=1,
+                                       lambda_view_baseline=-1, lambda_reprojection=1.0, lambda_parameter=0, val_epoch_freq=1,
+                                       print_freq=1, display_freq=100, save_epoch_freq=1, log_dir=None, resident_dataset=resident)
+        ft = DepthFineTuner(range_dir, list(range(NFRAMES)), params)
+        sd = default_init_state(0)
+        sd["pred_layer.weight"] = sd["pred_layer.weight"] * 0.1
+        sd["pred_layer.bias"] = torch.full((1,), math.log(2.0))
+        ft.model.load_state_dict(sd)
+        buf = io.StringIO()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(buf):
+            ft.fine_tune(writer=None)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        m = re.search(r"Epoch 0 took ([0-9.]+)s", buf.getvalue())
+        train_s = float(m.group(1)) if m else None
+        del ft
+        torch.cuda.empty_cache()
+        return {"pairs": n_pairs, "wall_s_total": wall, "train_loop_s": train_s,
+                "train_loop_pairs_per_s": (n_pairs / train_s) if train_s else None,
+                "loader": "HBM-resident clip" if resident else "file DataLoader, 4 workers (reference loader)",
+                "includes": "validation before and after (train-mode forward of all pairs + eval files), 35 steps, checkpoint"}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def run_reference_gpu(args):
     """`--impl reference-gpu`: the reference's GPU PyTorch path alone (same JSON shape as the other arms)."""
     if int(os.environ.get("RANK", 0)) != 0:
@@ -223,6 +322,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference-GPU-PyTorch leg (gpu_reference)")
+    ap.add_argument("--no-fine-tune-api", action="store_true", help="skip the DepthFineTuner.fine_tune() wall-clock leg and the multi-step parity number")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer pass")
     ap.add_argument("--workload", default="mc", choices=["mc", "monodepth2", "midas2"],
                     help="mc = BASELINE.json configs[1] (the headline); monodepth2 = configs C4's model at 192x640 BS4 per GPU "
@@ -372,6 +472,15 @@ def main():
         gpu_ref = gpu_reference(dev)
         gpu_ref["speedup_e2e_vs_tf32"] = (e2e["value"] if e2e else value) / gpu_ref["tf32"]["value"]
         gpu_ref["speedup_e2e_vs_fp32"] = (e2e["value"] if e2e else value) / gpu_ref["fp32"]["value"]
+    api = parity = None
+    if rank == 0 and world == 1 and args.workload == "mc" and not args.no_fine_tune_api:
+        try:
+            del step, dev_batches
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        api = {"resident": fine_tune_api(dev, args.precision, True), "file_loader": fine_tune_api(dev, args.precision, False)}
+        parity = parity_after_steps(dev)
     if rank == 0:
         print(json.dumps({
             "metric": metric, "value": value, "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -382,7 +491,8 @@ def main():
                        "global_batch": bs * world, "parallelism": f"dp{world}",
                        "l2_policy": "per-step working set (several GB of activations) >> 126 MB L2; no explicit flush",
                        "weights": weights},
-            "roofline": roofline, "roofline_loss_kernel": roof_loss, "cpu_baseline": cpu_base, "gpu_reference": gpu_ref, "e2e": e2e,
+            "roofline": roofline, "roofline_loss_kernel": roof_loss, "cpu_baseline": cpu_base, "gpu_reference": gpu_ref, "fine_tune_api": api,
+            "parity_after_steps": parity, "e2e": e2e,
             "gpu_launches": gpu_launches, "clocks": clocks, "final_loss": loss_last, "peaks_source": pk_src,
         }), flush=True)
     if world > 1:

@@ -44,31 +44,34 @@ __device__ __forceinline__ void accumulate16(const float* v, bool inside, int la
   }
 }
 
-// Called by the 128 epilogue threads (et = 0..127), all of them, after their last accumulate16.
-// sstat: [4 warps][2][cout] floats; last_flag: a shared-memory int; uses named barrier 1 (128 threads).
+// Called by ALL epilogue threads (et = 0 .. 32*NW-1) after their last accumulate16.
+// sstat: [NW warps][2][cout] floats; last_flag: a shared-memory int; uses named barrier BAR (32*NW threads).
+template <int NW = 4, int BAR = 1>
 __device__ __forceinline__ void finalize(const Stats& f, const float* sstat, int cout, int cout_valid, int et,
                                          volatile int* last_flag)
 {
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  for (int c = et; c < cout_valid; c += 128) {
+  constexpr int NT = 32 * NW;
+  auto sync = [] { asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NT) : "memory"); };
+  sync();
+  for (int c = et; c < cout_valid; c += NT) {
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) { s1 += sstat[(size_t)w * 2 * cout + c]; s2 += sstat[(size_t)w * 2 * cout + cout + c]; }
+    for (int w = 0; w < NW; ++w) { s1 += sstat[(size_t)w * 2 * cout + c]; s2 += sstat[(size_t)w * 2 * cout + cout + c]; }
     atomicAdd(f.scratch + 2 * c, (double)s1);
     atomicAdd(f.scratch + 2 * c + 1, (double)s2);
   }
   __threadfence();
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  sync();
   if (et == 0) {
     unsigned int* ticket = reinterpret_cast<unsigned int*>(f.scratch + 2 * 256);
     const int last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     *last_flag = last;
     if (last) *ticket = 0u;
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  sync();
   if (*last_flag) {
     __threadfence();
-    for (int c = et; c < cout_valid; c += 128) {
+    for (int c = et; c < cout_valid; c += NT) {
       const double sum = __ldcg(f.scratch + 2 * c), sq = __ldcg(f.scratch + 2 * c + 1);
       f.scratch[2 * c] = 0.0; f.scratch[2 * c + 1] = 0.0;
       const double mean = sum / (double)f.count;

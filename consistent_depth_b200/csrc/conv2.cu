@@ -32,7 +32,8 @@
 
 namespace {
 
-constexpr int kThreads = 32 * 7;
+constexpr int kEpiGroups = 2;                 // epilogue warp groups (4 warps = the 4 TMEM lane quarters each); M-tiles alternate
+constexpr int kThreads = 32 * (3 + 4 * kEpiGroups);
 constexpr int kMaxA = 12, kMaxB = 32;        // A stages: 1x1 convs need ~80 KB of activation loads in flight per SM to cover
                                                // the HBM latency (8 KB stages), k x k windows are 40-70 KB each (2 stages)
 constexpr int kAPad = 256;                     // zeroed bytes behind every A stage: a zero-weight (padded) tap of the last
@@ -70,9 +71,9 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* a_ring = smem;                                                      // NA x (a_stage_bytes + kAPad)
   uint8_t* b_ring = a_ring + (size_t)p.NA * (p.a_stage_bytes + kAPad);          // NB x b_tile_bytes
-  float* obuf = reinterpret_cast<float*>(b_ring + (size_t)p.NB * p.b_tile_bytes);   // [128][kOPitch]
-  float* sstat = obuf + 128 * kOPitch;                                         // [4][2][Cp]
-  float* sbias = sstat + 8 * p.Cp;                                             // [Cp] (zeros when the conv has no bias)
+  float* obuf = reinterpret_cast<float*>(b_ring + (size_t)p.NB * p.b_tile_bytes);   // [groups][128][kOPitch]
+  float* sstat = obuf + kEpiGroups * 128 * kOPitch;                            // [4 * groups warps][2][Cp]
+  float* sbias = sstat + kEpiGroups * 8 * p.Cp;                                             // [Cp] (zeros when the conv has no bias)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + p.Cp);
   uint64_t* a_full = bars;                      // [kMaxA]
   uint64_t* a_empty = a_full + kMaxA;           // [kMaxA]
@@ -83,7 +84,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
   uint32_t* tmem_base_sh = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (p.st.scratch) for (int i = threadIdx.x; i < 8 * p.Cp; i += kThreads) sstat[i] = 0.f;
+  if (p.st.scratch) for (int i = threadIdx.x; i < kEpiGroups * 8 * p.Cp; i += kThreads) sstat[i] = 0.f;
   for (int i = threadIdx.x; i < p.Cp; i += kThreads) sbias[i] = (p.bias && i < p.cout_valid) ? __ldg(p.bias + i) : 0.f;
   for (int i = threadIdx.x; i < p.NA * (kAPad / 16); i += kThreads)
     *reinterpret_cast<uint4*>(a_ring + (size_t)(i / (kAPad / 16)) * (p.a_stage_bytes + kAPad) + p.a_stage_bytes + (i % (kAPad / 16)) * 16) = make_uint4(0u, 0u, 0u, 0u);
@@ -91,7 +92,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.NA; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.NB; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 4 * kEpiGroups); }
     tc::mbar_fence_init();
   }
   if (warp == 2) { tc::tmem_alloc_dyn(tmem_base_sh, (uint32_t)p.tmem_cols); tc::tmem_relinquish(); }
@@ -191,11 +192,17 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
     }
   } else {
     // ============================ epilogue ============================
+    // Two groups of 4 warps; group g handles the M-tiles with (tile * MT + mt) % 2 == g, so two M-tiles are drained
+    // concurrently (one epilogue warp per scheduler is latency-bound: ~130 dependent instructions per 16-column chunk
+    // with the BatchNorm statistics).
     const int q = warp & 3;                          // TMEM lane quarter of this warp
+    const int grp = (warp - 3) >> 2;
     const int s = q * 32 + lane;                     // window slot of the M-tile held by this thread
     const int r = s / p.WS, sx = s - r * p.WS;
     const bool accum = (p.flags & 1) != 0, do_exp = (p.flags & 2) != 0;
-    float* orow = obuf + s * kOPitch;
+    float* orow = obuf + (grp * 128 + s) * kOPitch;
+    float* wstat = sstat + (size_t)(grp * 4 + q) * 2 * p.Cp;
+    const int bar_id = 1 + grp;
     int ti = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
       int t = tile;
@@ -206,6 +213,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
       tc::mbar_wait(&acc_full[buf], (uint32_t)((ti / p.nbuf) & 1));
       tc::tc_fence_after();
       for (int mt = 0; mt < p.MT; ++mt) {
+        if (((ti * p.MT + mt) & (kEpiGroups - 1)) != grp) continue;
         const int yy = oy + mt * p.R + r, xx = ox + sx;
         const bool inside = sx < p.VW && yy < p.Hv && xx < p.Wv;
         float* yp = p.y + ((size_t)n * p.HW + (inside ? (size_t)yy * p.Wv + xx : 0)) * p.y_ct;
@@ -217,7 +225,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
             // out[x] = sum_j D[x + j][j]: slot s adds its j-th block into row s - j (rows are distinct per j)
 #pragma unroll
             for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(orow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
             for (int j = 1; j < p.G; ++j) {
               tc::tmem_ld16(taddr + (uint32_t)(j * p.Cp + c16), v);
               if (sx >= j) {
@@ -229,7 +237,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
                   *reinterpret_cast<float4*>(tr + i) = o;
                 }
               }
-              asm volatile("bar.sync 1, 128;" ::: "memory");
+              asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
             }
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
@@ -244,7 +252,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
               v[i] += bq.x; v[i + 1] += bq.y; v[i + 2] += bq.z; v[i + 3] += bq.w;
             }
           }
-          if (p.st.scratch) bnepi::accumulate16(v, inside, lane, sstat + (size_t)q * 2 * p.Cp, p.Cp, c16);
+          if (p.st.scratch) bnepi::accumulate16(v, inside, lane, wstat, p.Cp, c16);
           if (!inside || c16 >= p.cout_valid) continue;
           if (do_exp) {
 #pragma unroll
@@ -268,7 +276,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
       if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);   // accumulator buffer free again
     }
     if (p.st.scratch)
-      bnepi::finalize(p.st, sstat, p.Cp, p.cout_valid, threadIdx.x - 96, reinterpret_cast<volatile int*>(tmem_base_sh + 1));
+      bnepi::finalize<4 * kEpiGroups, 3>(p.st, sstat, p.Cp, p.cout_valid, threadIdx.x - 96, reinterpret_cast<volatile int*>(tmem_base_sh + 1));
   }
 
   tc::tc_fence_before();
@@ -430,7 +438,7 @@ extern "C" int cvd_conv2_fwd(const void* z, int zc8, int zc8_off, const void* pa
     p.MT = mt; p.TR = mt * p.R; p.WR = p.TR + k - 1;
     p.plane_bytes = p.WR * p.WS * 16; p.a_stage_bytes = 4 * p.plane_bytes;
     p.b_tile_bytes = 64 * p.Ncols; p.b_tiles = p.nkb * k * p.ng;
-    const size_t fixed = 128 * kOPitch * 4 + 9 * p.Cp * 4 + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64 + 1024;
+    const size_t fixed = kEpiGroups * (128 * kOPitch * 4 + 8 * p.Cp * 4) + p.Cp * 4 + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64 + 1024;
     // weights resident in shared memory (1x1 convolutions): loaded once per CTA
     const size_t res_bytes = (size_t)p.b_tiles * p.b_tile_bytes;
     const bool allow_res = !(getenv("CVD2_NO_RESIDENT") && getenv("CVD2_NO_RESIDENT")[0] == '1');
@@ -475,7 +483,7 @@ extern "C" int cvd_conv2_fwd(const void* z, int zc8, int zc8_off, const void* pa
   CVD_CHECK_ARG(cr == CUDA_SUCCESS, "cvd_conv2_fwd: cuTensorMapEncodeTiled failed (%d) [Wv=%d Hv=%d zc8=%d N=%d WS=%d WR=%d]",
                 (int)cr, p.Wv, p.Hv, zc8, N, p.WS, p.WR);
 
-  const size_t smem = (size_t)p.NA * (p.a_stage_bytes + kAPad) + (size_t)p.NB * p.b_tile_bytes + 128 * kOPitch * 4 + 9 * p.Cp * 4 +
+  const size_t smem = (size_t)p.NA * (p.a_stage_bytes + kAPad) + (size_t)p.NB * p.b_tile_bytes + kEpiGroups * (128 * kOPitch * 4 + 8 * p.Cp * 4) + p.Cp * 4 +
                       (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64;
   const long long grid = p.ntiles < cvd_num_sms() ? p.ntiles : cvd_num_sms();
   static bool cfg = false;

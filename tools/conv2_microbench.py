@@ -97,7 +97,14 @@ def main():
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--only-big", action="store_true")
     ap.add_argument("--wgrad", action="store_true", help="weight-gradient kernels (conv_wgrad vs conv2_wgrad) instead")
+    ap.add_argument("--one", default=None, help="kind,cin,cout,k,H,W (kind = fwd | wgrad): run only this shape (for ncu)")
     a = ap.parse_args()
+    if a.one:
+        kind, ci, co, k, H, W = a.one.split(",")
+        ci, co, k, H, W = int(ci), int(co), int(k), int(H), int(W)
+        r = bench_wgrad(ci, co, k, H, W, a.N, a.reps) if kind == "wgrad" else bench_shape(ci, co, k, H, W, a.N, a.reps)
+        print(a.one, r)
+        return
     if a.wgrad:
         os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
         return main_wgrad(a)
