@@ -25,6 +25,7 @@
 // read-only path (it is L1/L2 resident: flow is spatially coherent); the
 // matching backward scatter uses fire-and-forget fp32 REDs that resolve in L2.
 #include "cvd_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -51,6 +52,26 @@ __device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.appro
 #endif
 constexpr int PIX = CVD_LOSS_PIX;   // pixels per thread, strided by the block size (lane <-> adjacent pixels)
 constexpr int LOSS_THREADS = 256;
+
+// fire-and-forget vector REDs (sm_90+: REDG.ADD.F32x2 / F32x4): one L1TEX/L2 request for two x-adjacent bilinear taps
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// the two x-adjacent taps (i, i+1) of one row: aligned pair -> v2; pair inside an aligned float4 -> v4 (zeros elsewhere);
+// straddling a 16-byte boundary or clamped at the image border -> scalars
+__device__ __forceinline__ void scatter_row(float* __restrict__ g, int i0, int i1, float v0, float v1) {
+  if (v0 == 0.f && v1 == 0.f) return;                  // masked-out pixel / zero-weight border taps
+  if (i1 == i0 + 1) {
+    const int a = i0 & 3;
+    if (!(a & 1)) { red_add_v2(g + i0, v0, v1); return; }
+    if (a == 1) { red_add_v4(g + i0 - 1, 0.f, v0, v1, 0.f); return; }
+  }
+  if (v0 != 0.f) atomicAdd(g + i0, v0);
+  if (v1 != 0.f) atomicAdd(g + i1, v1);
+}
 
 template <bool want_grad, bool do_r, bool do_d>
 __device__ __forceinline__ float pixel_term(
@@ -115,10 +136,8 @@ __device__ __forceinline__ float pixel_term(
       g = fmaf(k0, -mz * rq * rq, g);
       const float k1 = -k0 * rz * rz;                  // d|s|/d depth_tgt[tap] = -sg wt / z_w^2
       const float v00 = k1 * w00, v10 = k1 * w10, v01 = k1 * w01, v11 = k1 * w11;
-      if (v00 != 0.f) atomicAdd(grad_t + i00, v00);    // masked-out pixels and zero-weight border taps skip the RED
-      if (v10 != 0.f) atomicAdd(grad_t + i10, v10);
-      if (v01 != 0.f) atomicAdd(grad_t + i01, v01);
-      if (v11 != 0.f) atomicAdd(grad_t + i11, v11);
+      scatter_row(grad_t, i00, i10, v00, v10);          // vector REDs where the tap pair is 8- / 16-byte aligned
+      scatter_row(grad_t, i01, i11, v01, v11);
     }
   }
   return g;
@@ -239,6 +258,65 @@ consistency_kernel(const float* __restrict__ depth,
   }
 
   // block reduction of the four masked sums -> f64 accumulators acc[b][k][{r,d}]
+  float v0 = warp_sum(a_r[0]), v1 = warp_sum(a_d[0]), v2 = warp_sum(a_r[1]), v3 = warp_sum(a_d[1]);
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[wid][0] = v0; red[wid][1] = v1; red[wid][2] = v2; red[wid][3] = v3; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < LOSS_THREADS / 32; ++w) s += (double)red[w][threadIdx.x];
+    atomicAdd(acc + (size_t)b * 4 + threadIdx.x, s);
+  }
+}
+
+// Variant for W % 4 == 0 (every configuration of BASELINE.json): a thread owns 4 x-ADJACENT pixels, so its eight input
+// streams are 128-bit loads (8 LDG.128 instead of 32 LDG.32) and the direct gradient term is ONE vector RED per direction
+// instead of four scalar ones; the bilinear scatter uses the pair REDs above.  L1TEX requests per pixel pair drop from
+// ~26 to ~15 (the kernel is bound by L1TEX / RED throughput, profiles/r01_ncu_full_loss_v4_grad.csv).
+template <bool GRAD, bool DO_R, bool DO_D>
+__global__ void __launch_bounds__(LOSS_THREADS, 3)
+consistency_kernel_x4(const float* __restrict__ depth,
+                      const float* __restrict__ flow0, const float* __restrict__ flow1,
+                      const float* __restrict__ mask0, const float* __restrict__ mask1,
+                      const PairConst* __restrict__ consts, int H, int W,
+                      double* __restrict__ acc, float* __restrict__ grad)
+{
+  __shared__ PairConst pc;
+  __shared__ float red[LOSS_THREADS / 32][4];
+  const int b = blockIdx.y;
+  const int HW = H * W;
+  {
+    const float* src = reinterpret_cast<const float*>(consts + b);
+    float* dst = reinterpret_cast<float*>(&pc);
+    for (int i = threadIdx.x; i < (int)(sizeof(PairConst) / 4); i += LOSS_THREADS) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const float sxs = (float)W / (float)(W - 1), sys = (float)H / (float)(H - 1);
+  float a_r[2] = {0.f, 0.f}, a_d[2] = {0.f, 0.f};
+  const int p0 = (blockIdx.x * LOSS_THREADS + threadIdx.x) * 4;           // first of this thread's 4 pixels (same row: W % 4 == 0)
+  if (p0 < HW) {
+    const size_t o2 = (size_t)b * 2 * HW + p0, o1 = (size_t)b * HW + p0;
+    float4 dq[2], fuq[2], fvq[2], mq[2];
+    dq[0] = __ldcs(reinterpret_cast<const float4*>(depth + o2));   dq[1] = __ldcs(reinterpret_cast<const float4*>(depth + o2 + HW));
+    fuq[0] = __ldcs(reinterpret_cast<const float4*>(flow0 + o2));  fvq[0] = __ldcs(reinterpret_cast<const float4*>(flow0 + o2 + HW));
+    fuq[1] = __ldcs(reinterpret_cast<const float4*>(flow1 + o2));  fvq[1] = __ldcs(reinterpret_cast<const float4*>(flow1 + o2 + HW));
+    mq[0] = __ldcs(reinterpret_cast<const float4*>(mask0 + o1));   mq[1] = __ldcs(reinterpret_cast<const float4*>(mask1 + o1));
+    const int y = p0 / W, x0 = p0 - y * W;
+    const float yf = (float)y;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float dv[4] = {dq[k].x, dq[k].y, dq[k].z, dq[k].w}, fu[4] = {fuq[k].x, fuq[k].y, fuq[k].z, fuq[k].w};
+      const float fv[4] = {fvq[k].x, fvq[k].y, fvq[k].z, fvq[k].w}, mk[4] = {mq[k].x, mq[k].y, mq[k].z, mq[k].w};
+      float g[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        g[j] = pixel_term<GRAD, DO_R, DO_D>(pc.d[k], depth, grad, (b * 2 + 1 - k) * HW, (float)(x0 + j), yf,
+                                            dv[j], fu[j], fv[j], mk[j], W, W - 1, H - 1, sxs, sys, a_r[k], a_d[k]);
+      if (GRAD && (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f || g[3] != 0.f))
+        red_add_v4(grad + (size_t)(b * 2 + k) * HW + p0, g[0], g[1], g[2], g[3]);
+    }
+  }
   float v0 = warp_sum(a_r[0]), v1 = warp_sum(a_d[0]), v2 = warp_sum(a_r[1]), v3 = warp_sum(a_d[1]);
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) { red[wid][0] = v0; red[wid][1] = v1; red[wid][2] = v2; red[wid][3] = v3; }
@@ -383,7 +461,19 @@ extern "C" int cvd_consistency_fwd_bwd(const float* depth,
 #define CVD_LOSS_F(G, R, D) do { if (full) CVD_LOSS_LAUNCH(G, R, D, true); else CVD_LOSS_LAUNCH(G, R, D, false); } while (0)
 #define CVD_LOSS_D(G, R) do { if (dd) CVD_LOSS_F(G, R, true); else CVD_LOSS_F(G, R, false); } while (0)
 #define CVD_LOSS_R(G) do { if (dr) CVD_LOSS_D(G, true); else CVD_LOSS_D(G, false); } while (0)
-  if (gr) CVD_LOSS_R(true); else CVD_LOSS_R(false);
+  static const bool no_x4 = getenv("CVD_LOSS_X4") && getenv("CVD_LOSS_X4")[0] == '0';
+  const bool x4 = !no_x4 && (W & 3) == 0 && ((uintptr_t)depth & 15) == 0 && ((uintptr_t)flow0 & 15) == 0 && ((uintptr_t)flow1 & 15) == 0 &&
+                  ((uintptr_t)mask0 & 15) == 0 && ((uintptr_t)mask1 & 15) == 0 && (!grad_depth || ((uintptr_t)grad_depth & 15) == 0);
+  if (x4) {
+    dim3 grid4((unsigned)((HW / 4 + LOSS_THREADS - 1) / LOSS_THREADS), B);
+#define CVD_LOSS4_LAUNCH(G, R, D)                                                                      \
+  consistency_kernel_x4<G, R, D><<<grid4, LOSS_THREADS, 0, st>>>(depth, flow0, flow1, mask0, mask1, consts, H, W, acc, grad_depth)
+#define CVD_LOSS4_D(G, R) do { if (dd) CVD_LOSS4_LAUNCH(G, R, true); else CVD_LOSS4_LAUNCH(G, R, false); } while (0)
+#define CVD_LOSS4_R(G) do { if (dr) CVD_LOSS4_D(G, true); else CVD_LOSS4_D(G, false); } while (0)
+    if (gr) CVD_LOSS4_R(true); else CVD_LOSS4_R(false);
+  } else {
+    if (gr) CVD_LOSS_R(true); else CVD_LOSS_R(false);
+  }
   CVD_LAUNCH_OK("consistency_kernel");
   consistency_finalize<<<1, 128, 0, st>>>(acc, msum, intr, f0, f1, fg, f_dir_dev, lam_r, lam_b, B, B_global, out_pair, out_loss);
   CVD_LAUNCH_OK("consistency_finalize");

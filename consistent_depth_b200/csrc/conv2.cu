@@ -50,6 +50,7 @@ struct C2Args {
   int plane_bytes, a_stage_bytes, NA;
   int b_tile_bytes, NB, b_resident, b_tiles;   // b_tiles = weight tiles per CTA tile (nkb * k * ng)
   int nbuf, tmem_cols;
+  int a_split;                                 // 1: the window of a k-block is loaded as 4 boxes (plane x chunk) instead of one
   int flags;
   bnepi::Stats st;                             // st.scratch == nullptr: no fused BatchNorm statistics
 };
@@ -116,7 +117,11 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
           if (it >= p.NA) tc::mbar_wait(&a_empty[slot], (uint32_t)(((it / p.NA) - 1) & 1));
           tc::mbar_arrive_expect_tx(&a_full[slot], (uint32_t)p.a_stage_bytes);
           // box = (2*WS u64 per row, WR rows, 2 chunks, 1 image, 2 planes): [hi c0][hi c1][lo c0][lo c1], each [row][slot][16 B]
-          tma_load_5d(a_ring + (size_t)slot * (p.a_stage_bytes + kAPad), &zmap, 2 * ix0, iy0, p.zc8_off + 2 * kb, n, 0, &a_full[slot]);
+          uint8_t* dst = a_ring + (size_t)slot * (p.a_stage_bytes + kAPad);
+          if (!p.a_split) tma_load_5d(dst, &zmap, 2 * ix0, iy0, p.zc8_off + 2 * kb, n, 0, &a_full[slot]);
+          else
+            for (int q4 = 0; q4 < 4; ++q4)       // [hi c0][hi c1][lo c0][lo c1]: smaller requests interleave with the weight stream
+              tma_load_5d(dst + (size_t)q4 * p.plane_bytes, &zmap, 2 * ix0, iy0, p.zc8_off + 2 * kb + (q4 & 1), n, q4 >> 1, &a_full[slot]);
         }
       }
     }
@@ -455,7 +460,9 @@ extern "C" int cvd_conv2_fwd(const void* z, int zc8, int zc8_off, const void* pa
     for (int na = na_want; na >= 1 && !found; --na) {
       const long long left = (long long)smem_budget - (long long)fixed - (long long)na * (p.a_stage_bytes + kAPad);
       int nb = (int)(left / p.b_tile_bytes);
-      if (nb > 6) nb = 6;
+      int nb_cap = 16;
+      if (const char* e = getenv("CVD2_NB")) { const int v = atoi(e); if (v >= 2 && v <= kMaxB) nb_cap = v; }
+      if (nb > nb_cap) nb = nb_cap;
       if (nb >= 2) { p.b_resident = 0; p.NA = na; p.NB = nb; found = true; }
     }
     if (found) break;
@@ -475,7 +482,8 @@ extern "C" int cvd_conv2_fwd(const void* z, int zc8, int zc8_off, const void* pa
   alignas(64) CUtensorMap map;
   const cuuint64_t gdim[5] = {(cuuint64_t)(2 * p.Wv), (cuuint64_t)p.Hv, (cuuint64_t)zc8, (cuuint64_t)N, 2};
   const cuuint64_t gstr[4] = {(cuuint64_t)p.Wv * 16, (cuuint64_t)p.HW * 16, (cuuint64_t)zc8 * p.HW * 16, (cuuint64_t)N * zc8 * p.HW * 16};
-  const cuuint32_t box[5] = {(cuuint32_t)(2 * p.WS), (cuuint32_t)p.WR, 2, 1, 2};
+  p.a_split = (getenv("CVD2_ASPLIT") && getenv("CVD2_ASPLIT")[0] == '1') ? 1 : 0;
+  const cuuint32_t box[5] = {(cuuint32_t)(2 * p.WS), (cuuint32_t)p.WR, p.a_split ? 1u : 2u, 1, p.a_split ? 1u : 2u};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<void*>(z), gdim, gstr, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -27,7 +27,7 @@
 namespace {
 
 constexpr int kThreads = 32 * 6;           // warp 0 TMA producer, warp 1 MMA issuer (+TMEM), warps 2-5 epilogue
-constexpr int kStages = 2;
+constexpr int kMaxStages = 4;
 constexpr int kLeft = 16;                    // zero columns in front of a G tile's interior (>= k-1, keeps TMA destinations 128-B aligned)
 
 struct W2Args {
@@ -43,6 +43,7 @@ struct W2Args {
   int x_plane_bytes, g_plane_bytes, x_bytes, g_bytes, stage_bytes;   // per stage: [X hi][X lo][G hi][G lo]
   int n_sbo;                                // N-group stride of the G descriptor (16: shifted views; k == 1: chunk plane)
   int tmem_cols;
+  int nst;                                  // smem stages of the (X window, G tile) ring
 };
 
 __device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
@@ -59,10 +60,11 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
 {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stages = smem;
+  const int kStages = p.nst;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)kStages * p.stage_bytes);
-  uint64_t* full = bars;                 // [kStages]
-  uint64_t* empty = bars + kStages;      // [kStages]
-  uint64_t* acc_full = bars + 2 * kStages;
+  uint64_t* full = bars;                 // [kMaxStages]
+  uint64_t* empty = bars + kMaxStages;   // [kMaxStages]
+  uint64_t* acc_full = bars + 2 * kMaxStages;
   uint32_t* tmem_base_sh = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -259,6 +261,9 @@ extern "C" int cvd_conv2_wgrad(const void* xz, int xc8, int x_off, const void* g
   p.gch = round_up(cout, 16) / 8;
   CVD_CHECK_ARG(x_off >= 0 && x_off + nch_all <= xc8 && g_off >= 0 && g_off + p.gch <= gc8, "cvd_conv2_wgrad: channel range exceeds the operand planes");
   const int budget = 220 * 1024;
+  int kStages = 2;
+  if (const char* e = getenv("CVD2_WG_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= kMaxStages) kStages = v; }
+  p.nst = kStages;
   if (k == 1) {
     if (nch_all % 16 != 0 || round_up(cout, 16) > 256) return 2;             // M blocks of 128 input channels
     p.mblk = nch_all / 16; p.nch = 16; p.kyM = 1;
