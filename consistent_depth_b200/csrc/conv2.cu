@@ -102,26 +102,31 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_sh;
 
+  // Ring positions are RUNNING counters with an explicit wrap / phase bit: the issuer warp is a single thread whose
+  // scalar bookkeeping, not the tensor pipe, was the bound of the first version (ncu: ~250 instructions incl. four integer
+  // divisions per weight tile, tensor pipe 49 % active with no data waits).
   if (warp == 0) {
     // ============================ TMA producer: one k-block window (hi + lo planes) per stage ============================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&zmap)) : "memory");
-      int it = 0;
+      const int NA = p.NA, nkb = p.nkb, a_stride = p.a_stage_bytes + kAPad, tiles_x = p.tiles_x, tiles_y = p.tiles_y;
+      int slot = 0; uint32_t eph = 1u;                  // first pass over the ring: nothing to wait for
+      bool wrapped = false;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         int t = tile;
-        const int tx = t % p.tiles_x; t /= p.tiles_x;
-        const int ty = t % p.tiles_y; const int n = t / p.tiles_y;
+        const int tx = t % tiles_x; t /= tiles_x;
+        const int ty = t % tiles_y; const int n = t / tiles_y;
         const int iy0 = ty * p.TR - p.pad, ix0 = tx * p.VW - p.pad;
-        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-          const int slot = it % p.NA;
-          if (it >= p.NA) tc::mbar_wait(&a_empty[slot], (uint32_t)(((it / p.NA) - 1) & 1));
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (wrapped) tc::mbar_wait(&a_empty[slot], eph);
           tc::mbar_arrive_expect_tx(&a_full[slot], (uint32_t)p.a_stage_bytes);
           // box = (2*WS u64 per row, WR rows, 2 chunks, 1 image, 2 planes): [hi c0][hi c1][lo c0][lo c1], each [row][slot][16 B]
-          uint8_t* dst = a_ring + (size_t)slot * (p.a_stage_bytes + kAPad);
+          uint8_t* dst = a_ring + (size_t)slot * a_stride;
           if (!p.a_split) tma_load_5d(dst, &zmap, 2 * ix0, iy0, p.zc8_off + 2 * kb, n, 0, &a_full[slot]);
           else
             for (int q4 = 0; q4 < 4; ++q4)       // [hi c0][hi c1][lo c0][lo c1]: smaller requests interleave with the weight stream
               tma_load_5d(dst + (size_t)q4 * p.plane_bytes, &zmap, 2 * ix0, iy0, p.zc8_off + 2 * kb + (q4 & 1), n, q4 >> 1, &a_full[slot]);
+          if (++slot == NA) { slot = 0; if (wrapped) eph ^= 1u; else { wrapped = true; eph = 0u; } }
         }
       }
     }
@@ -129,19 +134,21 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
   } else if (warp == 1) {
     // ============================ weight streamer ============================
     if (lane == 0) {
+      const int b_tiles = p.b_tiles, NB = p.NB; const uint32_t tb = (uint32_t)p.b_tile_bytes;
       if (p.b_resident) {
-        for (int t = 0; t < p.b_tiles; ++t) {
-          tc::mbar_arrive_expect_tx(&b_full[t], (uint32_t)p.b_tile_bytes);
-          tc::bulk_g2s(b_ring + (size_t)t * p.b_tile_bytes, p.wp + (size_t)t * p.b_tile_bytes, (uint32_t)p.b_tile_bytes, &b_full[t]);
+        for (int t = 0; t < b_tiles; ++t) {
+          tc::mbar_arrive_expect_tx(&b_full[t], tb);
+          tc::bulk_g2s(b_ring + (size_t)t * tb, p.wp + (size_t)t * tb, tb, &b_full[t]);
         }
       } else {
-        int bt = 0;
+        int st = 0; uint32_t eph = 0u; bool wrapped = false;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-          for (int t = 0; t < p.b_tiles; ++t, ++bt) {
-            const int st = bt % p.NB;
-            if (bt >= p.NB) tc::mbar_wait(&b_empty[st], (uint32_t)(((bt / p.NB) - 1) & 1));
-            tc::mbar_arrive_expect_tx(&b_full[st], (uint32_t)p.b_tile_bytes);
-            tc::bulk_g2s(b_ring + (size_t)st * p.b_tile_bytes, p.wp + (size_t)t * p.b_tile_bytes, (uint32_t)p.b_tile_bytes, &b_full[st]);
+          const uint8_t* src = p.wp;
+          for (int t = 0; t < b_tiles; ++t, src += tb) {
+            if (wrapped) tc::mbar_wait(&b_empty[st], eph);
+            tc::mbar_arrive_expect_tx(&b_full[st], tb);
+            tc::bulk_g2s(b_ring + (size_t)st * tb, src, tb, &b_full[st]);
+            if (++st == NB) { st = 0; if (wrapped) eph ^= 1u; else wrapped = true; }
           }
         }
       }
@@ -149,51 +156,56 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
     __syncwarp();
   } else if (warp == 2) {
     // ============================ MMA issuer ============================
+    const int NA = p.NA, NB = p.NB, nkb = p.nkb, kk = p.k, ng = p.ng, MT = p.MT, nbuf = p.nbuf, resident = p.b_resident;
+    const uint32_t Ncols = (uint32_t)p.Ncols, tb = (uint32_t)p.b_tile_bytes;
     const uint32_t idesc = tc::idesc_bf16(128, p.Ncols, 0, 0);
     const uint32_t a_base = tc::smem_u32(a_ring), b_base = tc::smem_u32(b_ring);
     const uint64_t adesc0 = tc::smem_desc_base((uint32_t)p.plane_bytes, 128);      // LBO: next 8-channel chunk; SBO: next 8 slots
     const uint64_t bdesc0 = tc::smem_desc_base(128, 256);
-    const uint32_t lo_a = 2u * (uint32_t)p.plane_bytes, lo_b = 32u * (uint32_t)p.Ncols;
-    const uint32_t mt_stride = (uint32_t)(p.R * p.WS * 16);
-    int it = 0, bt = 0, ti = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
-      const int buf = ti % p.nbuf;
-      if (ti >= p.nbuf) { tc::mbar_wait(&acc_empty[buf], (uint32_t)(((ti / p.nbuf) - 1) & 1)); tc::tc_fence_after(); }
-      const uint32_t dbase = tmem_base + (uint32_t)(buf * p.MT * p.Ncols);
+    const uint32_t lo_a = 2u * (uint32_t)p.plane_bytes, lo_b = 32u * Ncols;
+    const uint32_t mt_stride = (uint32_t)(p.R * p.WS * 16), a_stride = (uint32_t)(p.a_stage_bytes + kAPad);
+    const uint32_t ky_stride = (uint32_t)(p.WS * 16), g_stride = (uint32_t)(p.G * 16);
+    int slot = 0, bst = 0, buf = 0; uint32_t aph = 0u, bph = 0u, cph = 1u; bool cwrapped = false;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      if (cwrapped) { tc::mbar_wait(&acc_empty[buf], cph); tc::tc_fence_after(); }
+      const uint32_t dbase = tmem_base + (uint32_t)(buf * MT) * Ncols;
       uint32_t acc = 0u;
-      for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-        const int slot = it % p.NA;
-        tc::mbar_wait(&a_full[slot], (uint32_t)((it / p.NA) & 1));
+      int ridx = 0;                                     // resident weights: tile index inside the CTA tile
+      for (int kb = 0; kb < nkb; ++kb) {
+        tc::mbar_wait(&a_full[slot], aph);
         tc::tc_fence_after();
-        const uint32_t sa = a_base + (uint32_t)slot * (uint32_t)(p.a_stage_bytes + kAPad);
-        for (int ky = 0; ky < p.k; ++ky) {
-          for (int g = 0; g < p.ng; ++g, ++bt) {
+        uint32_t a_ky = a_base + (uint32_t)slot * a_stride;
+        for (int ky = 0; ky < kk; ++ky, a_ky += ky_stride) {
+          uint32_t a_g = a_ky;
+          for (int g = 0; g < ng; ++g, a_g += g_stride) {
             int st;
-            if (p.b_resident) { st = (kb * p.k + ky) * p.ng + g; tc::mbar_wait(&b_full[st], 0u); }
-            else { st = bt % p.NB; tc::mbar_wait(&b_full[st], (uint32_t)((bt / p.NB) & 1)); }
+            if (resident) { st = ridx++; tc::mbar_wait(&b_full[st], 0u); }
+            else { st = bst; tc::mbar_wait(&b_full[st], bph); }
             tc::tc_fence_after();
             if (tc::elect_one()) {
-              const uint32_t bs = b_base + (uint32_t)st * p.b_tile_bytes;
+              const uint32_t bs = b_base + (uint32_t)st * tb;
               const uint64_t bd_hi = tc::smem_desc_at(bdesc0, bs), bd_lo = tc::smem_desc_at(bdesc0, bs + lo_b);
-              uint32_t a = sa + (uint32_t)((ky * p.WS + g * p.G) * 16);
-              uint32_t d = dbase;
-              for (int mt = 0; mt < p.MT; ++mt, a += mt_stride, d += (uint32_t)p.Ncols) {
+              uint32_t a = a_g, d = dbase;
+              for (int mt = 0; mt < MT; ++mt, a += mt_stride, d += Ncols) {
                 const uint64_t ad_hi = tc::smem_desc_at(adesc0, a);
                 tc::umma_f16(d, ad_hi, bd_hi, idesc, acc);
                 tc::umma_f16(d, tc::smem_desc_at(adesc0, a + lo_a), bd_hi, idesc, 1u);
                 tc::umma_f16(d, ad_hi, bd_lo, idesc, 1u);
               }
-              if (!p.b_resident) tc::umma_commit(&b_empty[st]);
+              if (!resident) tc::umma_commit(&b_empty[st]);
             }
             __syncwarp();
             acc = 1u;
+            if (!resident && ++bst == NB) { bst = 0; bph ^= 1u; }
           }
         }
         if (tc::elect_one()) tc::umma_commit(&a_empty[slot]);
         __syncwarp();
+        if (++slot == NA) { slot = 0; aph ^= 1u; }
       }
       if (tc::elect_one()) tc::umma_commit(&acc_full[buf]);
       __syncwarp();
+      if (++buf == nbuf) { buf = 0; if (cwrapped) cph ^= 1u; else { cwrapped = true; cph = 0u; } }
     }
   } else {
     // ============================ epilogue ============================
@@ -208,14 +220,13 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
     float* orow = obuf + (grp * 128 + s) * kOPitch;
     float* wstat = sstat + (size_t)(grp * 4 + q) * 2 * p.Cp;
     const int bar_id = 1 + grp;
-    int ti = 0;
+    int ti = 0, buf = 0; uint32_t fph = 0u;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++ti) {
       int t = tile;
       const int tx = t % p.tiles_x; t /= p.tiles_x;
       const int ty = t % p.tiles_y; const int n = t / p.tiles_y;
       const int oy = ty * p.TR, ox = tx * p.VW;
-      const int buf = ti % p.nbuf;
-      tc::mbar_wait(&acc_full[buf], (uint32_t)((ti / p.nbuf) & 1));
+      tc::mbar_wait(&acc_full[buf], fph);
       tc::tc_fence_after();
       for (int mt = 0; mt < p.MT; ++mt) {
         if (((ti * p.MT + mt) & (kEpiGroups - 1)) != grp) continue;
@@ -279,6 +290,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);   // accumulator buffer free again
+      if (++buf == p.nbuf) { buf = 0; fph ^= 1u; }
     }
     if (p.st.scratch)
       bnepi::finalize<4 * kEpiGroups, 3>(p.st, sstat, p.Cp, p.cout_valid, threadIdx.x - 96, reinterpret_cast<volatile int*>(tmem_base_sh + 1));
