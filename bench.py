@@ -500,39 +500,66 @@ def main():
 
 
 def measure_rooflines(model, step, batch, load, pk, pk_src):
-    """Per-launch CUDA-event timing of every tcgen05 conv (fwd + dgrad) launch of one un-graphed step, and of the
-    fused loss kernel.  achieved = algorithmic FLOPs (2*k*k*Cin*Cout*pixels, real channel counts) / event time."""
+    """Per-launch CUDA-event timing of every tcgen05 conv-family launch of one un-graphed, single-stream step (forward +
+    dgrad: conv2_kernel / conv_tc_kernel; weight gradient: wgrad2_kernel / wgrad_tc_kernel) and of the fused loss kernel.
+    achieved = algorithmic FLOPs (2*k*k*Cin*Cout*pixels, real channel counts) / event time."""
     from consistent_depth_b200 import ops
     recs = []
-    orig_conv = ops.conv
 
-    def timed_conv(src, packed, bias, dst, N, h, w, cin, cout, k, precision=3, flags=0, bn=None):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        orig_conv(src, packed, bias, dst, N, h, w, cin, cout, k, precision, flags, bn=bn)
-        b.record()
-        recs.append((a, b, 2.0 * k * k * cin * cout * N * h * w))
-    ops.conv = timed_conv
+    def wrap(name, fn, dims):
+        def timed(*a, **kw):
+            a0, b0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            r = fn(*a, **kw)
+            b0.record()
+            N, h, w, cin, cout, k = dims(a)
+            recs.append((name, a0, b0, 2.0 * k * k * cin * cout * N * h * w))
+            return r
+        return timed
+    orig = {n: getattr(ops, n) for n in ("conv", "conv2", "conv_wgrad", "conv2_wgrad")}
+    ops.conv = wrap("conv_tc_kernel (per-tap conv fwd + dgrad, first generation)", orig["conv"], lambda a: a[4:10])
+    ops.conv2 = wrap("conv2_kernel (TMA-fed kx-fused conv fwd + dgrad)", orig["conv2"], lambda a: a[5:11])
+    ops.conv_wgrad = wrap("wgrad_tc_kernel (per-tap weight gradient, first generation)", orig["conv_wgrad"], lambda a: a[3:9])
+    ops.conv2_wgrad = wrap("wgrad2_kernel (TMA-fed kx-fused / ky-stacked weight gradient)", orig["conv2_wgrad"], lambda a: a[5:11])
     multi = getattr(step.engine, "multi_stream", False)
     step.engine.multi_stream = False        # per-launch times: one kernel at a time (the timed steps fork branches)
+    reps = 3
     try:
         load(batch)
         step._snapshot_and_restore(step._fwd_bwd)       # warm
         recs.clear()
-        for _ in range(3):
+        for _ in range(reps):
             step._snapshot_and_restore(step._fwd_bwd)
         torch.cuda.synchronize()
     finally:
-        ops.conv = orig_conv
+        for n, f in orig.items():
+            setattr(ops, n, f)
         step.engine.multi_stream = multi
-    tot_ms = sum(a.elapsed_time(b) for a, b, _ in recs)
-    tot_fl = sum(f for _, _, f in recs)
-    ach = tot_fl / (tot_ms * 1e-3) / 1e12
     peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
-    roofline = {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv fwd + dgrad)", "bound": "tensor", "achieved": ach,
-                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "launches": len(recs) // 3,
-                "avg_launch_us": tot_ms * 1e3 / len(recs), "peak_src": pk_src + " (cuBLAS bf16 sustained)",
-                "note": "algorithmic fp32-equivalent FLOPs; the bf16x3 split issues 3 tensor-core MMAs per algorithmic MAC"}
+    fam = {}
+    for name, a0, b0, fl in recs:
+        f = fam.setdefault(name, [0.0, 0.0, 0])
+        f[0] += a0.elapsed_time(b0); f[1] += fl; f[2] += 1
+    by_kernel = {n: {"ms_per_step": v[0] / reps, "launches_per_step": v[2] // reps, "gflop_per_step": v[1] / reps / 1e9,
+                     "achieved_tflops": v[1] / (v[0] * 1e-3) / 1e12, "frac_of_bf16_peak": v[1] / (v[0] * 1e-3) / 1e12 / peak}
+                 for n, v in fam.items()}
+    dom = max(fam, key=lambda n: fam[n][0])
+    tot_ms, tot_fl, nl = fam[dom]
+    ach = tot_fl / (tot_ms * 1e-3) / 1e12
+    traffic = None
+    try:            # DRAM bytes of the dominant kernel's heaviest launch from the committed `ncu --set full` capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        traffic = tr.get(dom.split(" ")[0])
+    except Exception:
+        pass
+    all_ms, all_fl = sum(v[0] for v in fam.values()), sum(v[1] for v in fam.values())
+    roofline = {"kernel": dom, "bound": "tensor", "achieved": ach,
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "launches": nl // reps,
+                "avg_launch_us": tot_ms * 1e3 / nl, "peak_src": pk_src + " (cuBLAS bf16 sustained)",
+                "all_conv_kernels": {"achieved": all_fl / (all_ms * 1e-3) / 1e12, "frac": all_fl / (all_ms * 1e-3) / 1e12 / peak,
+                                     "ms_per_step": all_ms / reps},
+                "by_kernel": by_kernel,
+                "note": "algorithmic fp32-equivalent FLOPs; the bf16x3 split issues 3 tensor-core MMAs per algorithmic MAC (cap 1/3)"}
     # fused loss kernel at the bench workload (B=4, 224x384: 40 B/px/pair = 13.8 MB)
     from consistent_depth_b200.utils.geometry import fused_consistency
     depth = step.engine.depth.view(step.B, 2, H, W)

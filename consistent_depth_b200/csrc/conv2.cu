@@ -33,7 +33,11 @@
 namespace {
 
 constexpr int kEpiGroups = 2;                 // epilogue warp groups (4 warps = the 4 TMEM lane quarters each); M-tiles alternate
-constexpr int kThreads = 32 * (3 + 4 * kEpiGroups);
+constexpr int kIssuers = 2;                   // MMA issuer warps: the M-tiles of a CTA tile alternate between them (one thread
+                                               // issues ~1 UTCHMMA per 80 cycles incl. descriptor moves; N = 96 MMAs execute in 48)
+constexpr int kEpiWarp0 = 2 + kIssuers;       // first epilogue warp (a multiple of 4: TMEM lane quarter = warp % 4)
+constexpr int kThreads = 32 * (kEpiWarp0 + 4 * kEpiGroups);
+static_assert(kEpiWarp0 % 4 == 0, "epilogue warps must start at a multiple of 4");
 constexpr int kMaxA = 12, kMaxB = 32;        // A stages: 1x1 convs need ~80 KB of activation loads in flight per SM to cover
                                                // the HBM latency (8 KB stages), k x k windows are 40-70 KB each (2 stages)
 constexpr int kAPad = 256;                     // zeroed bytes behind every A stage: a zero-weight (padded) tap of the last
@@ -91,9 +95,9 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
     *reinterpret_cast<uint4*>(a_ring + (size_t)(i / (kAPad / 16)) * (p.a_stage_bytes + kAPad) + p.a_stage_bytes + (i % (kAPad / 16)) * 16) = make_uint4(0u, 0u, 0u, 0u);
   tc::fence_proxy_async_smem();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.NA; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < p.NB; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 4 * kEpiGroups); }
+    for (int i = 0; i < p.NA; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], kIssuers); }
+    for (int i = 0; i < p.NB; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], kIssuers); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], kIssuers); tc::mbar_init(&acc_empty[i], 4 * kEpiGroups); }
     tc::mbar_fence_init();
   }
   if (warp == 2) { tc::tmem_alloc_dyn(tmem_base_sh, (uint32_t)p.tmem_cols); tc::tmem_relinquish(); }
@@ -154,8 +158,9 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
       }
     }
     __syncwarp();
-  } else if (warp == 2) {
-    // ============================ MMA issuer ============================
+  } else if (warp < kEpiWarp0) {
+    // ============================ MMA issuers (warp 2 also owns TMEM) ============================
+    const int iw = warp - 2;                         // this issuer handles the M-tiles mt with mt % kIssuers == iw
     const int NA = p.NA, NB = p.NB, nkb = p.nkb, kk = p.k, ng = p.ng, MT = p.MT, nbuf = p.nbuf, resident = p.b_resident;
     const uint32_t Ncols = (uint32_t)p.Ncols, tb = (uint32_t)p.b_tile_bytes;
     const uint32_t idesc = tc::idesc_bf16(128, p.Ncols, 0, 0);
@@ -185,8 +190,8 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
             if (tc::elect_one()) {
               const uint32_t bs = b_base + (uint32_t)st * tb;
               const uint64_t bd_hi = tc::smem_desc_at(bdesc0, bs), bd_lo = tc::smem_desc_at(bdesc0, bs + lo_b);
-              uint32_t a = a_g, d = dbase;
-              for (int mt = 0; mt < MT; ++mt, a += mt_stride, d += Ncols) {
+              uint32_t a = a_g + (uint32_t)iw * mt_stride, d = dbase + (uint32_t)iw * Ncols;
+              for (int mt = iw; mt < MT; mt += kIssuers, a += kIssuers * mt_stride, d += kIssuers * Ncols) {
                 const uint64_t ad_hi = tc::smem_desc_at(adesc0, a);
                 tc::umma_f16(d, ad_hi, bd_hi, idesc, acc);
                 tc::umma_f16(d, tc::smem_desc_at(adesc0, a + lo_a), bd_hi, idesc, 1u);
@@ -213,7 +218,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
     // concurrently (one epilogue warp per scheduler is latency-bound: ~130 dependent instructions per 16-column chunk
     // with the BatchNorm statistics).
     const int q = warp & 3;                          // TMEM lane quarter of this warp
-    const int grp = (warp - 3) >> 2;
+    const int grp = (warp - kEpiWarp0) >> 2;
     const int s = q * 32 + lane;                     // window slot of the M-tile held by this thread
     const int r = s / p.WS, sx = s - r * p.WS;
     const bool accum = (p.flags & 1) != 0, do_exp = (p.flags & 2) != 0;
@@ -293,7 +298,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap zmap, const C2Args p)
       if (++buf == p.nbuf) { buf = 0; fph ^= 1u; }
     }
     if (p.st.scratch)
-      bnepi::finalize<4 * kEpiGroups, 3>(p.st, sstat, p.Cp, p.cout_valid, threadIdx.x - 96, reinterpret_cast<volatile int*>(tmem_base_sh + 1));
+      bnepi::finalize<4 * kEpiGroups, 3>(p.st, sstat, p.Cp, p.cout_valid, threadIdx.x - 32 * kEpiWarp0, reinterpret_cast<volatile int*>(tmem_base_sh + 1));
   }
 
   tc::tc_fence_before();

@@ -26,7 +26,8 @@
 
 namespace {
 
-constexpr int kThreads = 32 * 6;           // warp 0 TMA producer, warp 1 MMA issuer (+TMEM), warps 2-5 epilogue
+constexpr int kIssuers = 2;                // MMA issuer warps (k > 1: the accumulators of a pass alternate between them)
+constexpr int kThreads = 32 * 8;           // warp 0 TMA producer, warps 1-2 MMA issuers (warp 1 owns TMEM), warp 3 idle, warps 4-7 epilogue
 constexpr int kMaxStages = 4;
 constexpr int kLeft = 16;                    // zero columns in front of a G tile's interior (>= k-1, keeps TMA destinations 128-B aligned)
 
@@ -83,8 +84,8 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
     tc::fence_proxy_async_smem();
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    tc::mbar_init(acc_full, 1);
+    for (int i = 0; i < kStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], kIssuers); }
+    tc::mbar_init(acc_full, kIssuers);
     tc::mbar_fence_init();
   }
   if (warp == 1) { tc::tmem_alloc_dyn(tmem_base_sh, (uint32_t)p.tmem_cols); tc::tmem_relinquish(); }
@@ -126,8 +127,12 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ============================ MMA issuer ============================
+  } else if (warp <= kIssuers) {
+    // ============================ MMA issuers ============================
+    // k > 1: issuer iw owns the accumulators a0 + iw, a0 + iw + 2, ...; k == 1 (one accumulator per M block, every K step
+    // accumulates into it): only issuer 0 issues, the other keeps the barrier protocol
+    const int iw = warp - 1;
+    const int a_first = p.k > 1 ? a0 + iw : (iw == 0 ? a0 : a1), a_step = p.k > 1 ? kIssuers : 1;
     const uint32_t idesc = tc::idesc_bf16(128, p.NC, 1, 1);                  // both operands MN-major
     const uint32_t sbase = tc::smem_u32(stages);
     const uint64_t mdesc0 = tc::smem_desc_base(128, (uint32_t)p.KQ * 16);    // M groups: next chunk / next window row
@@ -142,8 +147,8 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
       if (tc::elect_one()) {
         const uint32_t xs = sbase + (uint32_t)st * p.stage_bytes;
         const uint32_t gs = xs + (uint32_t)p.x_bytes;
-        uint32_t dacc = tmem_base;
-        for (int a = a0; a < a1; ++a, dacc += (uint32_t)p.NC) {
+        uint32_t dacc = tmem_base + (uint32_t)((a_first - a0) * p.NC);
+        for (int a = a_first; a < a1; a += a_step, dacc += (uint32_t)(a_step * p.NC)) {
           uint32_t xa, ga;
           if (p.k > 1) {
             const int g = a / p.gch, c = a - g * p.gch;
@@ -171,7 +176,7 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
     }
     if (my_tiles > 0 && tc::elect_one()) tc::umma_commit(acc_full);
     __syncwarp();
-  } else if (my_tiles > 0) {
+  } else if (my_tiles > 0 && warp >= 4) {
     // ============================ epilogue: RED the partial dW ============================
     tc::mbar_wait(acc_full, 0);
     tc::tc_fence_after();

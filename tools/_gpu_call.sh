@@ -1,16 +1,4 @@
 mkdir -p gpurun_out
-run() { env $1 timeout 120 python tools/conv2_microbench.py --one $2 --reps 5 2>&1 | tail -1 | sed "s/^/[$1] /"; }
-for one in fwd,64,16,11,224,384 fwd,32,32,7,112,192 fwd,64,32,7,112,192; do
-  for e in "X=0" "CVD2_NB=3" "CVD2_NB=4" "CVD2_ASPLIT=1" "CVD2_MT=2" "CVD2_MT=2 CVD2_ASPLIT=1"; do run "$e" $one; done
-done 2>&1 | tee gpurun_out/r2_knobs1.log
-for one in wgrad,64,16,7,224,384 wgrad,64,16,11,224,384 wgrad,64,32,7,112,192 wgrad,32,32,5,112,192; do
-  for e in "CVD2_WG_STAGES=2" "CVD2_WG_STAGES=3" "CVD2_WG_STAGES=4" "CVD2_WG_GPP=1" "CVD2_WG_GPP=1 CVD2_WG_STAGES=3"; do run "$e" $one; done
-done 2>&1 | tee -a gpurun_out/r2_knobs1.log
-timeout 300 python -m pytest tests/test_consistency_gpu.py -m gpu -q 2>&1 | tail -3
-for e in "CVD_LOSS_X4=0" "CVD_LOSS_X4=1"; do env $e timeout 200 python tools/loss_microbench.py --sizes 224x384,1080x1920 --batches 4,16 --reps 10 2>&1 | python -c "
-import sys,json
-for l in sys.stdin:
-    try: d=json.loads(l)
-    except Exception: continue
-    print('$e', d['H'], d['B'], d['mode'], round(d['ms'],4), round(d['GBps']), round(d['frac_of_peak'],3))
-"; done 2>&1 | tee gpurun_out/r2_loss1.log
+timeout 600 python -m pytest tests/test_conv2_gpu.py tests/test_mc_gpu.py -m gpu -q --timeout 300 2>&1 | grep -v Warning | grep "^E \|passed\|failed\|FAILED" | head -30 > gpurun_out/r2_t8.log; cat gpurun_out/r2_t8.log
+timeout 900 python tools/conv2_microbench.py --out gpurun_out/r2_conv2_mb4.json > gpurun_out/r2_conv2_mb4.txt 2>&1; head -64 gpurun_out/r2_conv2_mb4.txt; tail -1 gpurun_out/r2_conv2_mb4.txt
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-roofline --no-gpu-reference --no-fine-tune-api 2>gpurun_out/r2_bench_err.log | tail -1 | tee gpurun_out/r2_bench7.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e'], d['final_loss'], d['gpu_launches'])"
