@@ -188,6 +188,7 @@ class McEngine:
         # kernel is small (<= 32 output channels: 2.2x on 64->16 11x11) and for 1x1 convs; with N >= 64 the per-tap kernel
         # already runs the tensor pipe at ~76 % and has no idle window lanes, so those k x k convs stay on it.
         self.v2_nmax = int(os.environ.get("CVD_CONV2_NMAX", "32"))
+        self.v2_all = os.environ.get("CVD_CONV2_ALL", "0") == "1"                  # A/B: every inception conv on the new kernels
         self.side_streams = []
         self.pmap, self.grad_flat = params.pmap, params.grad_flat
         self._p, self._g, self._rb = params._p, params._g, params._rb
@@ -220,6 +221,18 @@ class McEngine:
         t, rm, rv, gamma, beta, si = bn
         bns = ops.make_bn(self.conv_scratch[si], t.a, t.b, t.rstd, t.mean, gamma, beta, rm, rv)
         self.fwd.append(lambda: ops.conv2(z, zoff, pk, bias, d, N, h, w, cin, cout, k, 0, bns if self.train_mode else None))
+
+    def _use_conv2(self, k_gemm, n_gemm, k):
+        """Forward / dgrad dispatch of a k x k conv with GEMM K = k_gemm input and N = n_gemm output channels (measured,
+        tools/conv2_microbench.py on B200): few output channels or wide filters -> kx-fused kernel."""
+        if self.v2_all:
+            return True
+        return n_gemm <= 16 or (n_gemm <= self.v2_nmax and k >= 7) or (k >= 11 and k_gemm >= 64 and n_gemm <= k_gemm)
+
+    def _use_wgrad2(self, cin, cout, k):
+        """Weight-gradient dispatch: the TMA-fed kernel everywhere except more output than input channels (32 -> 64: 8 G
+        chunks x 3..7 ky rows make many passes over small maps)."""
+        return self.v2_all or not (cin < cout)
 
     def _gz_planes(self, C, h, w, slot):
         key = (C, h, w, slot)
@@ -344,7 +357,7 @@ class McEngine:
             mid.zsrc = (zmid, (aoff - o0) // 8)                # where this conv's input lives in the prepared planes
             self.fwd = []
             ko = boff - (o0 + A)
-            if v2 and Bs[i] <= self.v2_nmax:
+            if v2 and self._use_conv2(As[i], Bs[i], ks[i]):
                 self._conv2(zmid, (aoff - o0) // 8, f"{prefix}.convs.{i + 1}.3.weight", f"{prefix}.convs.{i + 1}.3.bias",
                             _T(buf, off=boff), As[i], Bs[i], ks[i], h, w, bn=(one, rmk[ko:ko + Bs[i]], rvk[ko:ko + Bs[i]], None, None, i))
             else:
@@ -461,9 +474,7 @@ class McEngine:
                     Wt = self._p(f"{prefix}.convs.{i + 1}.3.weight")
                     gs, xs = outs[i].bnbwd_src(), mids[i].src()
                     dW = self._g(f"{prefix}.convs.{i + 1}.3.weight")
-                    # wgrad dispatch (tools/conv2_microbench.py --wgrad, B200): the TMA-fed kernel wins for the wide filters
-                    # (2.3x on 64->16 11x11) and few channels; for 3x3 / 5x5 it is bound by L2->SM window traffic
-                    if v2 and self.v2_wgrad and ((ks[i] >= 7 and As[i] >= Bs[i]) or (As[i] <= 32 and Bs[i] <= 16)):
+                    if v2 and self.v2_wgrad and self._use_wgrad2(As[i], Bs[i], ks[i]):
                         zmid, xo = mids[i].zsrc
                         self.bwd.append(lambda zmid=zmid, xo=xo, gzk=gzk, go=boffs[i] // 8, gs=gs, xs=xs, dW=dW, ci=As[i], co=Bs[i], k=ks[i], h=h, w=w:
                                         ops.conv2_wgrad(zmid, xo, gzk, go, dW, N, h, w, ci, co, k) or
@@ -472,7 +483,7 @@ class McEngine:
                         self.bwd.append(lambda gs=gs, xs=xs, dW=dW, ci=As[i], co=Bs[i], k=ks[i], h=h, w=w:
                                         ops.conv_wgrad(gs, xs, dW, N, h, w, ci, co, k, prec))
                     d = ops.make_dst(mids[i].dview())
-                    if v2 and As[i] <= self.v2_nmax:
+                    if v2 and self._use_conv2(Bs[i], As[i], ks[i]):
                         pkt = torch.empty(ops.conv2_packed_bytes(Bs[i], As[i], ks[i]), dtype=torch.uint8, device=self.dev)
                         self.pack2_bwd.append((Wt, pkt, True))
                         self.bwd.append(lambda gzk=gzk, zo=boffs[i] // 8, pkt=pkt, d=d, ci=Bs[i], co=As[i], k=ks[i], h=h, w=w:

@@ -127,14 +127,15 @@ def test_mannequin_challenge_plan(fake_lib):
     assert e.forward(torch.rand(2, 3, 32, 48)).shape == (2, 32, 48)
     n_inc = sum(1 for k in mc_arch.state_dict_shapes() if k.endswith(".convs.0.0.weight"))
     assert n_inc == 22
-    # Dispatch: conv1 and the pred layer (3 / 1 channels) and the k x k convs with >= 64 GEMM-N channels stay on the
-    # first-generation per-tap kernel; the fused 1x1 convs and the k x k convs with <= 32 output channels run the TMA-fed
-    # kx-fused kernel.  Operands are prepared once: the block input (unless another block already prepared the same
+    # Dispatch: conv1 and the pred layer (3 / 1 channels) and the narrow-filter / many-output-channel k x k convs stay on
+    # the first-generation per-tap kernel; the fused 1x1 convs and the k x k convs with few output channels or wide filters
+    # run the TMA-fed kx-fused kernel.  Operands are prepared once: the block input (unless another block already prepared the same
     # tensor) and the 1x1 outputs a1|a2|a3.
     kk = [s_ for k_, s_ in mc_arch.state_dict_shapes().items() if ".convs." in k_ and k_.endswith(".3.weight")]
     assert len(kk) == 3 * n_inc
-    fwd_v2 = sum(1 for s_ in kk if s_[0] <= 32)                # (Cout, Cin, k, k): forward GEMM N = Cout
-    dgrad_v2 = sum(1 for s_ in kk if s_[1] <= 32)              # dgrad GEMM N = Cin
+    use2 = lambda kg, ng, k: ng <= 16 or (ng <= 32 and k >= 7) or (k >= 11 and kg >= 64 and ng <= kg)   # McEngine._use_conv2
+    fwd_v2 = sum(1 for s_ in kk if use2(s_[1], s_[0], s_[2]))      # (Cout, Cin, k, k): forward GEMM K = Cin, N = Cout
+    dgrad_v2 = sum(1 for s_ in kk if use2(s_[0], s_[1], s_[2]))    # dgrad GEMM K = Cout, N = Cin
     assert 0 < fwd_v2 < len(kk) and 0 < dgrad_v2 < len(kk)
     assert fake_lib.calls["cvd_conv_fwd"] + fake_lib.calls["cvd_conv_fwd_bn"] == 2 + len(kk) - fwd_v2
     assert fake_lib.calls["cvd_conv2_fwd"] == n_inc + fwd_v2
@@ -145,7 +146,7 @@ def test_mannequin_challenge_plan(fake_lib):
     e.backward(torch.rand(2, 32, 48))
     # weight gradients: the fused 1x1 convs and the wide / few-channel k x k convs on the operand planes (cvd_conv2_wgrad),
     # the rest (and conv1 / pred) on the fp32 views
-    wg_v2 = sum(1 for s_ in kk if (s_[2] >= 7 and s_[1] >= s_[0]) or (s_[1] <= 32 and s_[0] <= 16))   # McEngine's wgrad dispatch rule
+    wg_v2 = sum(1 for s_ in kk if not s_[1] < s_[0])             # McEngine._use_wgrad2
     assert 0 < wg_v2 < len(kk)
     assert fake_lib.calls["cvd_conv2_wgrad"] == n_inc + wg_v2 and fake_lib.calls["cvd_conv_wgrad"] == 2 + len(kk) - wg_v2
     # backward: one gradient-operand preparation per BatchNorm group (k x k outputs, 1x1 outputs); conv1 has no input gradient
