@@ -189,6 +189,12 @@ class McEngine:
         # already runs the tensor pipe at ~76 % and has no idle window lanes, so those k x k convs stay on it.
         self.v2_nmax = int(os.environ.get("CVD_CONV2_NMAX", "32"))
         self.v2_all = os.environ.get("CVD_CONV2_ALL", "0") == "1"                  # A/B: every inception conv on the new kernels
+        # Weight gradients feed nothing but Adam, so they leave the backward's critical path: every wgrad is enqueued on
+        # one of two side streams as soon as its operands exist and only joined at the end of backward(); inside the CUDA
+        # graph they overlap with the dgrad / BatchNorm-backward chain, in particular with the low-resolution levels whose
+        # kernels fill a fraction of the SMs.  Needs per-block gradient-operand planes (no shared scratch).
+        self.wg_async = os.environ.get("CVD_WGRAD_ASYNC", "1") == "1"
+        self.wg_streams = []
         self.side_streams = []
         self.pmap, self.grad_flat = params.pmap, params.grad_flat
         self._p, self._g, self._rb = params._p, params._g, params._rb
@@ -235,6 +241,8 @@ class McEngine:
         return self.v2_all or not (cin < cout)
 
     def _gz_planes(self, C, h, w, slot):
+        if self.wg_async:                # read by deferred weight gradients: one set of planes per block
+            return ops.z_alloc(self.N, C, h, w, self.dev)
         key = (C, h, w, slot)
         if key not in self._gz:
             self._gz[key] = ops.z_alloc(self.N, C, h, w, self.dev)
@@ -433,7 +441,7 @@ class McEngine:
                 dW, db = self._g("pred_layer.weight"), self._g("pred_layer.bias")
                 dld4, depth = self.dld4, self.depth
                 self.bwd.append(lambda: ops.dlogdepth(self.grad_depth, depth, dld4, db))
-                self.bwd.append(lambda gs=gs, xs=xs, dW=dW: ops.conv_wgrad(gs, xs, dW, N, H, W, 64, 1, 3, prec))
+                self.bwd.append(("wg", [lambda gs=gs, xs=xs, dW=dW: ops.conv_wgrad(gs, xs, dW, N, H, W, 64, 1, 3, prec)]))
                 d = ops.make_dst(z.dview())
                 fl = ops.FLAG_ACCUM if z.grad_written else 0
                 self.bwd.append(lambda gs=gs, pkt=pkt, d=d, fl=fl: ops.conv(gs, pkt, None, d, N, H, W, 1, 64, 3, prec, fl))
@@ -495,8 +503,13 @@ class McEngine:
                                         ops.conv(gs, pkt, None, d, N, h, w, ci, co, k, prec, 0))
                     kbranches.append([[self.bwd[0]], [self.bwd[1]]])
                     self.bwd = main_bwd
-                # wgrad and dgrad of each of the three convs: six independent kernels
-                self.bwd.append(("par", [b for pair in kbranches for b in pair]))
+                if self.wg_async:
+                    # the three weight gradients leave the critical path; the three dgrads stay parallel branches
+                    self.bwd.append(("wg", [pair[0][0] for pair in kbranches]))
+                    self.bwd.append(("par", [pair[1] for pair in kbranches]))
+                else:
+                    # wgrad and dgrad of each of the three convs: six independent kernels
+                    self.bwd.append(("par", [b for pair in kbranches for b in pair]))
                 db1 = self.grad_flat[self.pmap[f"{prefix}.convs.0.0.bias"][0]:][:o0 + A]
                 self.bwd.append(lambda buf=buf, dbuf=dbuf, a=a, b=b, rstd=rstd, mean=mean, bw=bw, db1=db1, cnt=o0 + A, npix=npix:
                                 ops.bn_bwd_reduce(buf, 0, cnt, dbuf, npix, scratch, a, b, rstd, mean, bw, True, dbias=db1))
@@ -526,10 +539,14 @@ class McEngine:
                         self.pack_bwd.append((W1, pkt, True))
                         dg = (lambda gs=gs, pkt=pkt, d=d, fl=fl, ci=o0 + A, co=cin, h=h, w=w:
                               ops.conv(gs, pkt, None, d, N, h, w, ci, co, 1, prec, fl))
-                    self.bwd.append(("par", [[wg], [dg]]))
+                    if self.wg_async:
+                        self.bwd.append(("wg", [wg]))
+                        self.bwd.append(dg)
+                    else:
+                        self.bwd.append(("par", [[wg], [dg]]))
                     x.grad_written = True
                 else:
-                    self.bwd.append(wg)
+                    self.bwd.append(("wg", [wg]))
             elif kind == "conv1":
                 _, img, t0 = rec
                 H, W = self.H, self.W
@@ -539,7 +556,7 @@ class McEngine:
                 self.bwd.append(lambda t0=t0: ops.bn_bwd_reduce(t0.buf, 0, 128, t0.dbuf, N * H * W, scratch, t0.a, t0.b, t0.rstd,
                                                                 t0.mean, t0.bw, True, gamma, beta, dg, dbt, dbias))
                 gs, xs, dW = t0.bnbwd_src(), img.src(), self._g("seq.0.weight")
-                self.bwd.append(lambda gs=gs, xs=xs, dW=dW: ops.conv_wgrad(gs, xs, dW, N, H, W, 3, 128, 7, prec))
+                self.bwd.append(("wg", [lambda gs=gs, xs=xs, dW=dW: ops.conv_wgrad(gs, xs, dW, N, H, W, 3, 128, 7, prec)]))
 
     # ------------------------------------------------------------------ execution
     def _run(self, plan):
@@ -547,9 +564,26 @@ class McEngine:
         forked onto side streams and joined back — inside the CUDA graph they become parallel branches, which
         keeps the SMs busy on the low-resolution hourglass levels whose kernels have fewer CTAs than the GPU has SMs."""
         main = None
+        wg_used = 0
         for op in plan:
             if not isinstance(op, tuple):
                 op()
+                continue
+            if op[0] == "wg":            # deferred weight gradients (see __init__): side stream, joined after the plan
+                if not (self.multi_stream and self.wg_async):
+                    for f in op[1]:
+                        f()
+                    continue
+                if main is None:
+                    main = torch.cuda.current_stream()
+                while len(self.wg_streams) < 2:
+                    self.wg_streams.append(torch.cuda.Stream(device=self.dev))
+                for f in op[1]:
+                    sw = self.wg_streams[wg_used % 2]
+                    wg_used += 1
+                    sw.wait_stream(main)
+                    with torch.cuda.stream(sw):
+                        f()
                 continue
             branches = op[1]
             if not self.multi_stream or len(branches) == 1:
@@ -575,6 +609,9 @@ class McEngine:
                     f()
             for i in range(len(branches) - 1):
                 main.wait_stream(self.side_streams[i])
+        if wg_used:
+            for sw in self.wg_streams:
+                main.wait_stream(sw)
 
     def forward(self, images):
         """images (N,3,H,W) BGR in [0,1] (CUDA, contiguous) -> depth (N,H,W) (engine-owned buffer)."""

@@ -1,5 +1,6 @@
 """GPU: cvd_flow_consistency_masks against the oracle and the golden masks the reference's
-utils/consistency.py produced.  Opt-in because the kernel was written after the round's GPU budget was spent."""
+utils/consistency.py produced.  Masks are thresholded float quantities: pixels whose value sits within rounding of a
+threshold may flip between implementations, so the bar is a mismatch FRACTION (reported on failure), not equality."""
 import os
 
 import numpy as np
@@ -21,4 +22,6 @@ def test_flow_consistency_masks_match_reference(name):
     want = fo.consistent_flow_masks(flows, colors, ft, ct)
     for d in range(2):
         assert masks[d].shape == (H, W) and masks[d].dtype == bool
-        assert (masks[d] != want[d]).mean() <= 2e-3 and (masks[d] != g[f"{name}_mask{d}"]).mean() <= 2e-3
+        mo, mg = float((masks[d] != want[d]).mean()), float((masks[d] != g[f"{name}_mask{d}"]).mean())
+        og = float((want[d] != g[f"{name}_mask{d}"]).mean())          # oracle on this host vs the reference-generated golden
+        assert mo <= 2e-3 and mg <= 2e-3, f"direction {d}: kernel vs oracle {mo:.2e}, kernel vs golden {mg:.2e}, oracle vs golden {og:.2e}"

@@ -1,5 +1,11 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_conv2_gpu.py tests/test_mc_gpu.py -m gpu -q --timeout 300 2>&1 | grep -v Warning | grep "^E \|passed\|failed\|FAILED" | head -30 > gpurun_out/r2_t9.log; cat gpurun_out/r2_t9.log
-timeout 900 python tools/conv2_microbench.py --out gpurun_out/r2_conv2_mb5.json > gpurun_out/r2_conv2_mb5.txt 2>&1; head -34 gpurun_out/r2_conv2_mb5.txt | cut -c1-110; tail -1 gpurun_out/r2_conv2_mb5.txt
-timeout 900 python tools/conv2_microbench.py --wgrad --out gpurun_out/r2_wgrad2_mb2.json > gpurun_out/r2_wgrad2_mb2.txt 2>&1; cat gpurun_out/r2_wgrad2_mb2.txt | cut -c1-110
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-roofline --no-gpu-reference --no-fine-tune-api 2>gpurun_out/r2_bench_err.log | tail -1 | tee gpurun_out/r2_bench8.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e'], d['final_loss'], d['gpu_launches'])"
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 2>&1 | grep -v Warning | tail -15 > gpurun_out/r2_pytest_full1.log; tail -8 gpurun_out/r2_pytest_full1.log
+timeout 300 python tools/profile_engine.py --workload mc --out gpurun_out/r2_mc_ops_v7.json 2>&1 | tail -16
+timeout 900 python bench.py --steps 30 --warmup 5 2>gpurun_out/r2_bench_full_err.log | tail -1 > gpurun_out/r2_bench_full1.json; python -c "
+import json; d=json.load(open('gpurun_out/r2_bench_full1.json'))
+print(d['value'], d['ms_per_step'], d['e2e'], d['final_loss'])
+print('roofline', {k:d['roofline'][k] for k in ('kernel','achieved','frac','launches')}, d['roofline']['all_conv_kernels'])
+for k,v in d['roofline']['by_kernel'].items(): print('  ',k[:30], v)
+print('loss roof', d['roofline_loss_kernel'])
+print('cpu', d['cpu_baseline']); print('gpu_ref', d['gpu_reference']); print('api', d['fine_tune_api']); print('parity', d['parity_after_steps']); print(d['clocks'])
+"; tail -5 gpurun_out/r2_bench_full_err.log
