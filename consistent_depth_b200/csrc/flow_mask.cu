@@ -5,7 +5,6 @@
 // sample = bilinear at (x + u - 0.5, y + v - 0.5), border-clamped (grid = 2 uv / (W, H) - 1 and F.grid_sample with
 // align_corners=False, padding_mode="border": utils/consistency.py:8-24 -- note the (W, H) normalisation, unlike
 // utils/geometry.py:201-208 which divides by (W-1, H-1)).
-// NOT YET VALIDATED ON HARDWARE (written after the round's GPU budget was spent): tests/test_flowmask_gpu.py is opt-in.
 #include <cuda_runtime.h>
 #include <stdint.h>
 

@@ -16,7 +16,8 @@ class _ParamL1Fn(torch.autograd.Function):
         grads = []
         for p, p0 in zip(params, inits):
             g = torch.zeros_like(p)
-            _lib.check(L.cvd_param_l1(_lib.ptr(p.detach().contiguous()), _lib.ptr(p0.contiguous()),
+            pc, p0c = p.detach().contiguous(), p0.contiguous()      # named: temporaries must outlive the launch's argument list
+            _lib.check(L.cvd_param_l1(_lib.ptr(pc), _lib.ptr(p0c),
                                       C.c_longlong(p.numel()), C.c_float(lam), _lib.ptr(g), _lib.ptr(out),
                                       _lib.stream()), "cvd_param_l1")
             grads.append(g)

@@ -2,7 +2,7 @@
 (`consistent_flow_masks(flows, colors, flow_thresh, color_thresh)` on numpy (H,W,2) / (H,W,3) arrays, list of two
 bool masks back), computed by one CUDA kernel (cvd_flow_consistency_masks) instead of numpy + F.grid_sample on the CPU.
 `consistent_flow_masks_batched` is the tensor-level entry for a whole clip resident on the GPU.
-Not yet validated on hardware (tests/test_flowmask_gpu.py is opt-in)."""
+Validated on a B200 against the oracle and the reference-generated golden masks (tests/test_flowmask_gpu.py)."""
 import ctypes as C
 
 import numpy as np
@@ -16,7 +16,11 @@ def consistent_flow_masks_batched(flows, colors, flow_thresh, color_thresh):
     B, _, _, H, W = flows.shape
     assert colors.shape == (B, 2, 3, H, W)
     masks = torch.empty(B, 2, H, W, device=flows.device)
-    _lib.check(_lib.lib().cvd_flow_consistency_masks(_lib.ptr(flows.contiguous()), _lib.ptr(colors.contiguous()), _lib.ptr(masks),
+    # keep the contiguous copies alive across the launch: a temporary created inside the argument list is returned to the
+    # caching allocator before the next argument is evaluated, and `colors.contiguous()` then reuses the block `flows` was
+    # copied to (found on hardware: masks computed from overwritten flows)
+    flows, colors = flows.contiguous(), colors.contiguous()
+    _lib.check(_lib.lib().cvd_flow_consistency_masks(_lib.ptr(flows), _lib.ptr(colors), _lib.ptr(masks),
                                                      B, H, W, C.c_float(flow_thresh), C.c_float(color_thresh), _lib.stream()),
                "cvd_flow_consistency_masks")
     return masks

@@ -368,7 +368,7 @@ int cvd_recip_relu_bwd(const float* ddepth, const float* depth, const float* raw
 
 
 /* ------------------------------------------------------------------------------------------------
- * SURVEY §8(f) rank 3 (not yet validated on hardware): the flow + photometric consistency masks of
+ * the flow + photometric consistency masks of
  * utils/consistency.py:53-67 (flow.py:199-228) for B frame pairs, both directions, in one launch.
  * flows (B, 2 directions, 2, H, W): [b,0] = flow frame0 -> frame1, [b,1] = flow frame1 -> frame0 (pixels);
  * colors (B, 2 frames, 3, H, W); masks (B, 2 directions, H, W) float {0, 1}.
@@ -377,7 +377,7 @@ int cvd_flow_consistency_masks(const float* flows, const float* colors, float* m
                                float flow_thresh, float color_thresh, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * SURVEY §8(f) rank 4 (not yet run on hardware): the FlowNet2 custom ops, forward only, NCHW fp32.
+ * the FlowNet2 custom ops, forward only, NCHW fp32 (run on a B200 against the oracle).
  * cvd_correlation_fwd  = correlation_package (correlation_cuda_kernel.cu:51-128; FlowNetC.py:28-31 uses pad = md = 20,
  *                        K = 1, s1 = 1, s2 = 2): out (B, D*D, Ho, Wo), D = 2 (md / s2) + 1, sizes from cvd_correlation_out_size
  * cvd_resample2d_fwd   = resample2d_package (resample2d_kernel.cu:17-73, kernel_size 1, bilinear): out = in1 sampled at (x + flow_x, y + flow_y)
