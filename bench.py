@@ -547,15 +547,15 @@ def measure_rooflines(model, step, batch, load, pk, pk_src):
     dom = max(fam, key=lambda n: fam[n][0])
     tot_ms, tot_fl, nl = fam[dom]
     ach = tot_fl / (tot_ms * 1e-3) / 1e12
-    traffic = None
+    traffic = traffic_note = None
     try:            # DRAM bytes of the dominant kernel's heaviest launch from the committed `ncu --set full` capture
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
-        traffic = tr.get(dom.split(" ")[0])
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(dom.split(" ")[0])
+        traffic, traffic_note = tr["dram_bytes"], tr["note"]
     except Exception:
         pass
     all_ms, all_fl = sum(v[0] for v in fam.values()), sum(v[1] for v in fam.values())
     roofline = {"kernel": dom, "bound": "tensor", "achieved": ach,
-                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "launches": nl // reps,
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_note": traffic_note, "launches": nl // reps,
                 "avg_launch_us": tot_ms * 1e3 / nl, "peak_src": pk_src + " (cuBLAS bf16 sustained)",
                 "all_conv_kernels": {"achieved": all_fl / (all_ms * 1e-3) / 1e12, "frac": all_fl / (all_ms * 1e-3) / 1e12 / peak,
                                      "ms_per_step": all_ms / reps},

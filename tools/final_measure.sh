@@ -9,7 +9,7 @@ CVD_PROFILE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_durat
 python tools/summarize_launches.py gpurun_out/${R}_launches_bench_ncu.csv --steps 2 > gpurun_out/${R}_launch_summary.json; head -30 gpurun_out/${R}_launch_summary.json
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv2_kernel -s 3 -c 1 -o gpurun_out/${R}_ncu_conv2_fwd_k11 python tools/conv2_microbench.py --one fwd,64,16,11,224,384 --reps 2 > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:wgrad2_kernel -s 3 -c 1 -o gpurun_out/${R}_ncu_wgrad2_k11 python tools/conv2_microbench.py --one wgrad,64,16,11,224,384 --reps 2 > /dev/null 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:consistency_kernel -s 8 -c 1 -o gpurun_out/${R}_ncu_loss_grad python tools/loss_microbench.py --sizes 1080x1920 --batches 16 --reps 3 --warmup 2 > /dev/null 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:consistency_kernel -s 2 -c 1 -o gpurun_out/${R}_ncu_loss_grad python tools/loss_microbench.py --sizes 1080x1920 --batches 16 --reps 3 --warmup 2 > /dev/null 2>&1
 timeout 900 python tools/loss_microbench.py --batches 1,2,4,8,16,32,64 --reps 20 --out gpurun_out/${R}_loss_microbench.json > gpurun_out/${R}_loss_microbench.log 2>&1; tail -3 gpurun_out/${R}_loss_microbench.log | cut -c1-200
 timeout 600 python tools/conv2_microbench.py --out gpurun_out/${R}_conv2_microbench.json > gpurun_out/${R}_conv2_microbench.txt 2>&1; tail -1 gpurun_out/${R}_conv2_microbench.txt
 timeout 600 python tools/conv2_microbench.py --wgrad --out gpurun_out/${R}_wgrad2_microbench.json > gpurun_out/${R}_wgrad2_microbench.txt 2>&1; tail -1 gpurun_out/${R}_wgrad2_microbench.txt
