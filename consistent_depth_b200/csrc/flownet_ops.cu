@@ -2,8 +2,8 @@
 // The reference builds them for sm_50..sm_70 only (third_party/flownet2/networks/*_package/setup.py).  One thread per
 // output element over flownet_ops_core.h; these maps are 1/8-resolution feature maps (correlation: 441 x C MACs per
 // pixel, < 1 GFLOP per frame pair), so no tiling is attempted.
-// NOT YET RUN ON HARDWARE (written after the round's GPU budget was spent): the arithmetic is checked on the host
-// (tests/test_flownet_ops_core_cpu.py); tests/test_flownet_ops_gpu.py is opt-in.
+// Run on a B200 against the oracle (tests/test_flownet_ops_gpu.py); the arithmetic is also checked on the host
+// (tests/test_flownet_ops_core_cpu.py).
 #include <cuda_runtime.h>
 
 #include "../../include/cvd.h"

@@ -1,5 +1,4 @@
-"""GPU: the FlowNet2 custom ops on sm_100a against the oracle.  Opt-in because the
-kernels were written after the round's GPU budget was spent (their arithmetic is checked on the host by
+"""GPU: the FlowNet2 custom ops on sm_100a against the oracle (their arithmetic is also checked on the host by
 tests/test_flownet_ops_core_cpu.py)."""
 import os
 
