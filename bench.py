@@ -461,7 +461,7 @@ def main():
         roofline, roof_loss = measure_rooflines(model, step, dev_batches[0], load, pk, pk_src)
 
     cpu_base = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:       # rank 0 at N = 1 only (the other arms report it at N > 1)
         threads = host_cpus()
         v, sec, done = cpu_reference_steps(3, 1, threads, budget_s=60.0)
         cpu_base = {"value": v, "unit": "frame-pairs/s", "cores": threads, "kind": "port",

@@ -24,7 +24,7 @@ from . import midas_arch as arch
 from .mono2_engine import Mono2Engine, Mono2Params, _Act, _BN, _plain
 
 CHUNK = 64          # channel width of one block-diagonal launch of a grouped conv
-BRANCHES = 4        # the chunk launches of one grouped conv are independent: forked onto this many graph branches
+BRANCHES = int(__import__("os").environ.get("CVD_MIDAS_BRANCHES", "8"))   # the chunk launches of one grouped conv are independent: forked onto this many graph branches
 
 
 class MidasParams(Mono2Params):

@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-timeout 200 python tools/debug_flowmask.py 2>&1 | tail -30 | tee gpurun_out/r2_flowmask_dbg.log
-timeout 200 python -m pytest tests/test_flowmask_gpu.py tests/test_consistency_gpu.py -m gpu -q 2>&1 | grep "^E \|passed\|failed" | head
+for b in 4 8 16; do
+CVD_MIDAS_BRANCHES=$b timeout 300 python bench.py --workload midas2 --steps 8 --warmup 3 --no-e2e 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('branches $b', d['value'], d['ms_per_step'])"
+done 2>&1 | tee gpurun_out/r2_midas_branches.log
