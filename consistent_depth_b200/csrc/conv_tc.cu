@@ -62,6 +62,10 @@ struct ConvArgs {
   // fused BatchNorm(train) statistics of the conv output (NULL scratch: off)
   double* st_scratch; const float* st_gamma; const float* st_beta; float* st_rm; float* st_rv;
   float* st_a; float* st_b; float* st_rstd; float* st_mean; float st_eps, st_mom; long long st_count;
+  // chunked launch: blockIdx.y = chunk j, an independent conv of the same shape whose source / destination views
+  // (with bias and BatchNorm arrays) sit j * ch_src / j * ch_dst channels further, weights j * ch_wp bytes further and
+  // statistics scratch j * ch_scratch doubles further (grouped-conv chunks, 256-column chunks of a wide Cout)
+  int ch_src, ch_dst, ch_scratch; long long ch_wp;
 };
 
 __device__ __forceinline__ int view_phys(int c, int c0, int n0, int gap) { return c0 + c + (c >= n0 ? gap : 0); }
@@ -84,7 +88,14 @@ conv_tc_kernel(const ConvArgs p)
   uint64_t* acc_empty = acc_full + 2;            // [2]
   uint32_t* tmem_base_sh = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* sparams = reinterpret_cast<float*>(bars + 32);           // per-channel constants, 5 x cin floats
-  fillns::stage_params(p.src, sparams, p.cin, threadIdx.x, kThreads);
+  const int chunk = (int)blockIdx.y;
+  fillns::SrcView sv = p.src;
+  sv.c0 += chunk * p.ch_src; sv.dy_c0 += chunk * p.ch_src;
+  const int dshift = chunk * p.ch_dst;
+  const uint8_t* const wp = p.wp + (size_t)chunk * p.ch_wp;
+  const float* const bias = p.bias ? p.bias + dshift : nullptr;
+  const int y_c0 = p.y_c0 + dshift;
+  fillns::stage_params(sv, sparams, p.cin, threadIdx.x, kThreads);
   float* sstat = sparams + 5 * p.cin;                              // [4 epilogue warps][2][cout] column sums / sums of squares
   if (p.st_scratch) for (int i = threadIdx.x; i < 8 * p.cout; i += kThreads) sstat[i] = 0.f;
 
@@ -193,7 +204,7 @@ conv_tc_kernel(const ConvArgs p)
           const int kbg = min(kGroupCh, p.cin - g64 * kGroupCh) >> 4;       // k-blocks of the pack group
           const int kb0 = p.gsplit == 2 ? (g & 1) * 2 : 0;                  // first k-block of this item
           const int nks = (item_chunks(g) >> 1) / p.kbs;
-          const uint8_t* gsrc = p.wp + (size_t)g64 * taps * (kGroupCh / 16) * p.kb_bytes;
+          const uint8_t* gsrc = wp + (size_t)g64 * taps * (kGroupCh / 16) * p.kb_bytes;
           for (int tap = 0; tap < taps; ++tap) {
             for (int ks = 0; ks < nks; ++ks, ++issued) {
               if (issued >= p.nstages) {
@@ -221,7 +232,7 @@ conv_tc_kernel(const ConvArgs p)
       for (int g = 0; g < p.ngroups; ++g, ++item) {
         const int slot = item % p.nslots;
         if (item >= p.nslots) tc::mbar_wait(&a_empty[slot], (uint32_t)(((item / p.nslots) - 1) & 1));
-        fillns::fill_window<kProducerThreads>(p.src, a_slots + (size_t)slot * p.slot_bytes, p.plane_bytes, p.gchunks * p.plane_bytes, p.nsplit,
+        fillns::fill_window<kProducerThreads>(sv, a_slots + (size_t)slot * p.slot_bytes, p.plane_bytes, p.gchunks * p.plane_bytes, p.nsplit,
                             n, p.H, p.W, oy - p.pad, ox - p.pad, p.HP, p.WP, item_cfirst(g), item_chunks(g), tid, sparams, p.cin);
         tc::fence_proxy_async_smem();
         tc::mbar_arrive(&a_full[slot]);
@@ -251,9 +262,9 @@ conv_tc_kernel(const ConvArgs p)
         for (int c16 = 0; c16 < p.cout; c16 += 16) {
           float v[16];
           tc::tmem_ld16(taddr + (uint32_t)c16, v);    // warp-collective: executed by all lanes
-          if (p.bias) {
+          if (bias) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) if (c16 + i < p.cout_valid) v[i] += __ldg(p.bias + c16 + i);
+            for (int i = 0; i < 16; ++i) if (c16 + i < p.cout_valid) v[i] += __ldg(bias + c16 + i);
           }
           if (p.st_scratch) bnepi::accumulate16(v, inside, lane, sstat + (size_t)q * 2 * p.cout, p.cout, c16);
           if (!inside || c16 >= p.cout_valid) continue;
@@ -261,7 +272,7 @@ conv_tc_kernel(const ConvArgs p)
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = expf(v[i]);
           }
-          float* dst = yp + view_phys(c16, p.y_c0, p.y_n0, p.y_gap);
+          float* dst = yp + view_phys(c16, y_c0, p.y_n0, p.y_gap);
           if (c16 + 16 <= p.cout_valid) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
@@ -279,8 +290,10 @@ conv_tc_kernel(const ConvArgs p)
       if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);   // accumulator buffer free for tile ti + 2
     }
     if (p.st_scratch) {
-      const bnepi::Stats st{p.st_scratch, p.st_gamma, p.st_beta, p.st_rm, p.st_rv, p.st_a, p.st_b, p.st_rstd, p.st_mean,
-                            p.st_eps, p.st_mom, p.st_count};
+      const bnepi::Stats st{p.st_scratch + (size_t)chunk * p.ch_scratch, p.st_gamma ? p.st_gamma + dshift : nullptr,
+                            p.st_beta ? p.st_beta + dshift : nullptr, p.st_rm ? p.st_rm + dshift : nullptr,
+                            p.st_rv ? p.st_rv + dshift : nullptr, p.st_a + dshift, p.st_b + dshift, p.st_rstd + dshift,
+                            p.st_mean + dshift, p.st_eps, p.st_mom, p.st_count};
       bnepi::finalize(st, sstat, p.cout, p.cout_valid, threadIdx.x - 32 * (kIssuers + 9),
                       reinterpret_cast<volatile int*>(tmem_base_sh + 1));   // (static smem would exceed the 227 KB opt-in)
     }
@@ -397,11 +410,17 @@ extern "C" int cvd_conv_pack_batch(const void* descs_dev, int n, int precision, 
 
 static int conv_fwd_impl(const cvd_src_t* src, const void* packed_w, const float* bias,
                          const cvd_dst_t* dst, int N, int H, int W, int cin, int cout, int k,
-                         int precision, int flags, const cvd_bn_t* bn, void* stream)
+                         int precision, int flags, const cvd_bn_t* bn, void* stream,
+                         int nchunks = 1, int ch_src = 0, int ch_dst = 0, long long ch_wp = 0)
 {
   if (cout > 256) {
-    // more output channels than one launch's TMEM accumulator holds: 256-column chunks (see pack_one)
+    // more output channels than one launch's TMEM accumulator holds: 256-column chunks (see pack_one) -- one chunked
+    // launch (blockIdx.y = chunk) when the chunks are uniform, else one launch per chunk
     CVD_CHECK_ARG(src && dst && packed_w, "cvd_conv_fwd: null pointer");
+    CVD_CHECK_ARG(nchunks == 1, "cvd_conv_fwd_chunks: cout must be <= 256");
+    if (cout % 256 == 0 && dst->gap == 0 && !getenv("CVD_CONV_NO_CHUNKS"))
+      return conv_fwd_impl(src, packed_w, bias, dst, N, H, W, cin, 256, k, precision, flags, bn, stream, cout / 256, 0, 256,
+                           (long long)cvd_conv_packed_bytes(cin, 256, k, precision));
     for (int c0 = 0; c0 < cout; c0 += 256) {
       const int cc = cout - c0 < 256 ? cout - c0 : 256;
       cvd_dst_t d = *dst;
@@ -447,6 +466,10 @@ static int conv_fwd_impl(const cvd_src_t* src, const void* packed_w, const float
     p.st_a = bn->a + dst->c_off; p.st_b = bn->b + dst->c_off; p.st_rstd = bn->rstd + dst->c_off; p.st_mean = bn->mean + dst->c_off;
     p.st_eps = bn->eps; p.st_mom = bn->momentum; p.st_count = (long long)N * H * W;
   }
+  CVD_CHECK_ARG(nchunks >= 1 && nchunks <= 65535, "cvd_conv_fwd_chunks: nchunks=%d", nchunks);
+  CVD_CHECK_ARG(nchunks == 1 || (src->gap == 0 && src->dy_gap == 0 && dst->gap == 0 && (ch_src & 3) == 0 && (ch_dst & 3) == 0),
+                "cvd_conv_fwd_chunks: chunked launches need gap-free, 4-channel aligned views");
+  p.ch_src = ch_src; p.ch_dst = ch_dst; p.ch_wp = ch_wp; p.ch_scratch = 2 * 256 + 1;   // = cvd_bn_scratch_bytes(256) / 8
   p.N = N; p.H = H; p.W = W; p.k = k; p.pad = (k - 1) / 2;
   p.cin = round_up(cin, 16); p.cout = round_up(cout, 16);
   CVD_CHECK_ARG(p.cout <= 256, "cvd_conv_fwd: cout=%d > 256", cout);
@@ -469,7 +492,7 @@ static int conv_fwd_impl(const cvd_src_t* src, const void* packed_w, const float
     for (int ci = 0; ci < 6 && !found; ++ci) {
       const int mtx = cand[ci][0], mty = cand[ci][1];
       if (2 * mtx * mty * p.cout > 512) continue;
-      if ((long long)N * ((W + 8 * mtx - 1) / (8 * mtx)) * ((H + 16 * mty - 1) / (16 * mty)) < min_tiles) continue;
+      if ((long long)nchunks * N * ((W + 8 * mtx - 1) / (8 * mtx)) * ((H + 16 * mty - 1) / (16 * mty)) < min_tiles) continue;
       if (8 * mtx > round_up(W, 8) && mtx > 1) continue;
       if (16 * mty > round_up(H, 16) && mty > 1) continue;
       const int HP = 16 * mty + k - 1, WP = 8 * mtx + k - 1;
@@ -513,7 +536,9 @@ static int conv_fwd_impl(const cvd_src_t* src, const void* packed_w, const float
   CVD_CHECK_ARG(p.plane_bytes < (1 << 18) && p.WP * 16 < (1 << 18), "cvd_conv_fwd: descriptor offset overflow");
 
   const size_t smem = (size_t)p.nslots * p.slot_bytes + (size_t)p.nstages * p.stage_bytes + 1024 + fillns::param_bytes(p.cin) + 32 * p.cout;
-  const long long grid = p.ntiles < cvd_num_sms() ? p.ntiles : cvd_num_sms();   // persistent: one CTA per SM
+  // persistent: one CTA per SM (chunked launch: the SMs are divided between the chunks)
+  long long grid = (cvd_num_sms() + nchunks - 1) / nchunks;
+  if (grid > p.ntiles) grid = p.ntiles;
   const int MT = p.mtx * p.mty;
   cudaError_t e = cudaSuccess;
 #define CVD_CONV_LAUNCH(MTV, NS)                                                                             \
@@ -523,7 +548,7 @@ static int conv_fwd_impl(const cvd_src_t* src, const void* packed_w, const float
       e = cudaFuncSetAttribute(conv_tc_kernel<MTV, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)); \
       cfg = true;                                                                                            \
     }                                                                                                        \
-    if (e == cudaSuccess) conv_tc_kernel<MTV, NS><<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(p); \
+    if (e == cudaSuccess) conv_tc_kernel<MTV, NS><<<dim3((unsigned)grid, (unsigned)nchunks), kThreads, smem, (cudaStream_t)stream>>>(p); \
   } while (0)
 #define CVD_CONV_MT(NS)                                                                                      \
   do {                                                                                                       \
@@ -549,4 +574,14 @@ extern "C" int cvd_conv_fwd_bn(const cvd_src_t* src, const void* packed_w, const
 {
   CVD_CHECK_ARG(bn != nullptr, "cvd_conv_fwd_bn: bn is NULL");
   return conv_fwd_impl(src, packed_w, bias, dst, N, H, W, cin, cout, k, precision, flags, bn, stream);
+}
+
+extern "C" int cvd_conv_fwd_chunks(const cvd_src_t* src, const void* packed_w, const float* bias,
+                                   const cvd_dst_t* dst, int N, int H, int W, int cin, int cout, int k,
+                                   int precision, int flags, const cvd_bn_t* bn,
+                                   int nchunks, int src_shift, int dst_shift, long long packed_stride, void* stream)
+{
+  CVD_CHECK_ARG(cout <= 256, "cvd_conv_fwd_chunks: cout=%d > 256", cout);
+  return conv_fwd_impl(src, packed_w, bias, dst, N, H, W, cin, cout, k, precision, flags, bn, stream,
+                       nchunks, src_shift, dst_shift, packed_stride);
 }

@@ -35,6 +35,7 @@ struct WgArgs {
   int dw_ci_stride;                                // Cin of the whole dW tensor (>= cin_w when this launch is a chunk)
   int zb_ci, zb_co, tot_cin, tot_cout;             // blockIdx.z enumerates 256 x 256 blocks of a larger dW (1, 1: single block)
   int group;                                       // > 0: grouped conv chunk, dW is (Cout, group, k, k): only same-group entries are kept
+  int diag;                                        // > 0: blockIdx.z enumerates the diagonal chunks of a grouped conv (chunk = cin_w channels)
   int nsplit;
   int x_is_m;                   // 1: M = X channels (Cin), N = G channels (Cout)
   int Mrows, mblk;              // MMA M (64/128), number of M blocks
@@ -55,7 +56,12 @@ wgrad_tc_kernel(const WgArgs p)
   SrcView xv = p.x, gv = p.g;
   int cin_w = p.cin_w, cout_w = p.cout_w;
   float* dwp = p.dw;
-  if (p.zb_ci * p.zb_co > 1) {
+  if (p.diag > 0) {
+    // grouped conv: chunk z of the block-diagonal weight -- both operands and the dW rows shift by z chunks
+    const int c0 = (int)blockIdx.z * cin_w;
+    xv.c0 += c0; xv.dy_c0 += c0; gv.c0 += c0; gv.dy_c0 += c0;
+    dwp += (size_t)c0 * p.group * p.k * p.k;
+  } else if (p.zb_ci * p.zb_co > 1) {
     const int ci0 = cib * 256, co0 = cob * 256;
     xv.c0 += ci0; xv.dy_c0 += ci0; gv.c0 += co0; gv.dy_c0 += co0;       // (chunked launches require gap-free views)
     cin_w = min(256, p.tot_cin - ci0); cout_w = min(256, p.tot_cout - co0);
@@ -218,7 +224,7 @@ int cvd_conv_wgrad_kx(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oi
 
 static int wgrad_impl(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oihw,
                       int N, int H, int W, int cin, int cout, int k, int precision, int dw_ci_stride, void* stream, int group = 0,
-                      int tot_cin = 0, int tot_cout = 0);
+                      int tot_cin = 0, int tot_cout = 0, int diag_chunks = 0);
 
 extern "C" int cvd_conv_wgrad_grouped(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_ogkk,
                                       int N, int H, int W, int c, int group_size, int k, int precision, void* stream)
@@ -226,6 +232,18 @@ extern "C" int cvd_conv_wgrad_grouped(const cvd_src_t* gsrc, const cvd_src_t* xs
   CVD_CHECK_ARG(gsrc && xsrc && dw_ogkk && gsrc->x && xsrc->x, "cvd_conv_wgrad_grouped: null pointer");
   CVD_CHECK_ARG(c > 0 && c <= 256 && group_size > 0 && c % group_size == 0, "cvd_conv_wgrad_grouped: c=%d group_size=%d", c, group_size);
   return wgrad_impl(gsrc, xsrc, dw_ogkk, N, H, W, c, c, k, precision, -1, stream, group_size);
+}
+
+extern "C" int cvd_conv_wgrad_grouped_chunks(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_ogkk,
+                                             int N, int H, int W, int c, int nchunks, int group_size, int k, int precision,
+                                             void* stream)
+{
+  CVD_CHECK_ARG(gsrc && xsrc && dw_ogkk && gsrc->x && xsrc->x, "cvd_conv_wgrad_grouped_chunks: null pointer");
+  CVD_CHECK_ARG(c > 0 && c <= 256 && c % 16 == 0 && group_size > 0 && c % group_size == 0 && nchunks >= 1 && nchunks <= 65535,
+                "cvd_conv_wgrad_grouped_chunks: c=%d group_size=%d nchunks=%d", c, group_size, nchunks);
+  CVD_CHECK_ARG(gsrc->gap == 0 && xsrc->gap == 0 && gsrc->dy_gap == 0 && xsrc->dy_gap == 0,
+                "cvd_conv_wgrad_grouped_chunks: gap-free views required");
+  return wgrad_impl(gsrc, xsrc, dw_ogkk, N, H, W, c, c, k, precision, -1, stream, group_size, 0, 0, nchunks);
 }
 
 extern "C" int cvd_conv_wgrad(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oihw,
@@ -246,7 +264,7 @@ extern "C" int cvd_conv_wgrad(const cvd_src_t* gsrc, const cvd_src_t* xsrc, floa
 
 static int wgrad_impl(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oihw,
                       int N, int H, int W, int cin, int cout, int k, int precision, int dw_ci_stride, void* stream, int group,
-                      int tot_cin, int tot_cout)
+                      int tot_cin, int tot_cout, int diag_chunks)
 {
   CVD_CHECK_ARG(precision == 1 || precision == 3, "cvd_conv_wgrad: precision must be 1 or 3");
   CVD_CHECK_ARG(k >= 1 && k <= 11 && (k & 1), "cvd_conv_wgrad: k=%d unsupported", k);
@@ -268,7 +286,8 @@ static int wgrad_impl(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_oi
   p.tot_cin = tot_cin > 0 ? tot_cin : cin; p.tot_cout = tot_cout > 0 ? tot_cout : cout;
   p.zb_ci = (p.tot_cin + 255) / 256; p.zb_co = (p.tot_cout + 255) / 256;
   if (tot_cin <= 0) { p.zb_ci = 1; p.zb_co = 1; }
-  const int zb = p.zb_ci * p.zb_co;
+  p.diag = diag_chunks;
+  const int zb = diag_chunks > 0 ? diag_chunks : p.zb_ci * p.zb_co;
   p.nsplit = precision;
   CVD_CHECK_ARG(p.cin <= 256 && p.cout <= 256, "cvd_conv_wgrad: channel counts above 256 unsupported");
   p.x_is_m = p.cin >= p.cout;

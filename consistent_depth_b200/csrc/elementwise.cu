@@ -385,7 +385,8 @@ inline unsigned ew_grid(long long total) {
 
 }  // namespace
 
-extern "C" size_t cvd_bn_scratch_bytes(int C) { return (size_t)(2 * C + 1) * sizeof(double); }
+// one block of [2 x 256 sums | ticket] per 256 channels: chunked conv launches accumulate their chunks concurrently
+extern "C" size_t cvd_bn_scratch_bytes(int C) { return (size_t)((C + 255) / 256 > 0 ? (C + 255) / 256 : 1) * (2 * 256 + 1) * sizeof(double); }
 
 extern "C" int cvd_bn_stats(const float* x, int c_total, int c_off, int C, long long npix, void* scratch,
                             const float* gamma, const float* beta, float eps, float momentum,

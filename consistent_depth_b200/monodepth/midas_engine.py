@@ -24,7 +24,9 @@ from . import midas_arch as arch
 from .mono2_engine import Mono2Engine, Mono2Params, _Act, _BN, _plain
 
 CHUNK = 64          # channel width of one block-diagonal launch of a grouped conv
-BRANCHES = int(__import__("os").environ.get("CVD_MIDAS_BRANCHES", "8"))   # the chunk launches of one grouped conv are independent: forked onto this many graph branches
+CHUNK_LAUNCH = __import__("os").environ.get("CVD_MIDAS_CHUNK_LAUNCH", "1") != "0"   # grouped conv: all chunks in one launch
+# CHUNK_LAUNCH off: the chunk launches of one grouped conv are independent and forked onto this many graph branches
+BRANCHES = int(__import__("os").environ.get("CVD_MIDAS_BRANCHES", "8"))
 
 
 class MidasParams(Mono2Params):
@@ -58,14 +60,34 @@ class MidasEngine(Mono2Engine):
         self.raw_outputs[wkey[:-7]] = dst
         self.fwd.append(lambda: ops.conv(src, pk, bias, d, N, h, w, cin, cout, k, prec, flags))
 
+    def _chunk_packs(self, Wt, width, gs, flip, table):
+        """One contiguous packed buffer for all CHUNK x CHUNK block-diagonal chunks of a grouped weight."""
+        nb = ops.packed_bytes(CHUNK, CHUNK, 3, self.prec)
+        pk = torch.empty(nb * (width // CHUNK), dtype=torch.uint8, device=self.dev)
+        for j in range(width // CHUNK):
+            table.append((Wt[j * CHUNK:(j + 1) * CHUNK], pk[j * nb:(j + 1) * nb], flip, CHUNK, gs))
+        return pk, nb
+
     def _grouped_fwd(self, y1, bn1, wkey, dst, width, h, w, bn2):
-        """conv2 of a Bottleneck: grouped 3x3 of relu(bn1(y1)) -> dst, CHUNK channels per launch."""
+        """conv2 of a Bottleneck: grouped 3x3 of relu(bn1(y1)) -> dst, as width / CHUNK block-diagonal CHUNK-channel
+        convs in ONE chunked launch (blockIdx.y = chunk; CVD_MIDAS_CHUNK_LAUNCH=0: one launch per chunk on BRANCHES streams)."""
         gs = width // arch.GROUPS
         Wt = self._p(wkey)
         N, prec = self.N, self.prec
+        nch = width // CHUNK
+        if CHUNK_LAUNCH:
+            pk, nb = self._chunk_packs(Wt, width, gs, False, self.pack_fwd)
+            s = ops.make_src(ops.View(y1, 0), bn1.a, bn1.b, True)
+            d = ops.make_dst(ops.View(dst, 0))
+            fused = bn2.fused if bn2 is not None else None
+            self.fwd.append(lambda: ops.conv_chunks(s, pk, None, d, N, h, w, CHUNK, CHUNK, 3, nch, CHUNK, CHUNK, nb, prec, 0,
+                                                    bn=fused if self.train_mode else None))
+            if bn2 is not None:
+                self._bn_eval(bn2)
+            return
         branches = [[] for _ in range(BRANCHES)]
         scratches = [bn2.scratch] + [ops.bn_scratch(self.dev) for _ in range(BRANCHES - 1)] if bn2 is not None else None
-        for j in range(width // CHUNK):
+        for j in range(nch):
             c0 = j * CHUNK
             pk = self._packed(CHUNK, CHUNK, 3)
             self.pack_fwd.append((Wt[c0:c0 + CHUNK], pk, False, CHUNK, gs))
@@ -86,8 +108,18 @@ class MidasEngine(Mono2Engine):
         gs = width // arch.GROUPS
         Wt, dW = self._p(wkey), self._g(wkey)
         N, prec = self.N, self.prec
+        nch = width // CHUNK
+        if CHUNK_LAUNCH:
+            g0 = g_of_chunk(0)
+            x0 = ops.make_src(ops.View(y1, 0), bn1.a, bn1.b, True)
+            pk, nb = self._chunk_packs(Wt, width, gs, True, self.pack_bwd)
+            d = ops.make_dst(ops.View(d1, 0))
+            self.bwd.append(("par", [
+                [lambda: ops.conv_wgrad_grouped_chunks(g0, x0, dW, N, h, w, CHUNK, nch, gs, 3, prec)],
+                [lambda: ops.conv_chunks(g0, pk, None, d, N, h, w, CHUNK, CHUNK, 3, nch, CHUNK, CHUNK, nb, prec, 0)]]))
+            return
         branches = [[] for _ in range(BRANCHES)]
-        for j in range(width // CHUNK):
+        for j in range(nch):
             c0 = j * CHUNK
             g = g_of_chunk(c0)
             x = ops.make_src(ops.View(y1, c0), bn1.a, bn1.b, True)

@@ -110,7 +110,8 @@ class _BN:
         self.gamma, self.beta = eng._p(prefix + ".weight"), eng._p(prefix + ".bias")
         self.dgamma, self.dbeta = eng._g(prefix + ".weight"), eng._g(prefix + ".bias")
         self.rm, self.rv = eng._rb(prefix + ".running_mean"), eng._rb(prefix + ".running_var")
-        self.scratch = ops.bn_scratch(eng.dev)
+        # one statistics block per 64-channel chunk: chunked launches (grouped conv, Cout > 256) reduce concurrently
+        self.scratch = ops.bn_scratch(eng.dev, max(256, 4 * C))
         self.fused = ops.make_bn(self.scratch, self.a, self.b, self.rstd, self.mean, self.gamma, self.beta, self.rm, self.rv)
 
 

@@ -89,6 +89,16 @@ def conv(src, packed, bias, dst, N, H, W, cin, cout, k, precision=3, flags=0, bn
                                        N, H, W, cin, cout, k, precision, flags, _lib.stream()), "cvd_conv_fwd")
 
 
+def conv_chunks(src, packed, bias, dst, N, H, W, cin, cout, k, nchunks, src_shift, dst_shift, packed_stride,
+                precision=3, flags=0, bn=None):
+    """nchunks same-shape convs in one launch: chunk j = views shifted by j*src_shift / j*dst_shift channels, weights
+    at packed + j*packed_stride bytes (bn: scratch from bn_scratch(device, 256 * nchunks))."""
+    _lib.check(_lib.lib().cvd_conv_fwd_chunks(C.byref(src), _lib.ptr(packed), _lib.ptr(bias), C.byref(dst),
+                                              N, H, W, cin, cout, k, precision, flags, C.byref(bn) if bn is not None else None,
+                                              nchunks, src_shift, dst_shift, C.c_longlong(packed_stride), _lib.stream()),
+               "cvd_conv_fwd_chunks")
+
+
 def conv_wgrad(gsrc, xsrc, dw, N, H, W, cin, cout, k, precision=3):
     """dw (fp32 OIHW, pre-zeroed or accumulating) += G (x) X."""
     _lib.check(_lib.lib().cvd_conv_wgrad(C.byref(gsrc), C.byref(xsrc), _lib.ptr(dw), N, H, W, cin, cout, k,
@@ -285,6 +295,12 @@ def channel_sum(x, c_off, Cn, out):
 def conv_wgrad_grouped(gsrc, xsrc, dw_rows, N, H, W, c, group_size, k, precision=3):
     _lib.check(_lib.lib().cvd_conv_wgrad_grouped(C.byref(gsrc), C.byref(xsrc), _lib.ptr(dw_rows), N, H, W, c, group_size, k,
                                                  precision, _lib.stream()), "cvd_conv_wgrad_grouped")
+
+
+def conv_wgrad_grouped_chunks(gsrc, xsrc, dw, N, H, W, c, nchunks, group_size, k, precision=3):
+    """All chunks of a grouped conv's weight gradient in one launch; gsrc / xsrc: views of chunk 0, dw: whole gradient."""
+    _lib.check(_lib.lib().cvd_conv_wgrad_grouped_chunks(C.byref(gsrc), C.byref(xsrc), _lib.ptr(dw), N, H, W, c, nchunks,
+                                                        group_size, k, precision, _lib.stream()), "cvd_conv_wgrad_grouped_chunks")
 
 
 def pack_weights_grouped(w_rows, c, group_size, transpose_flip=False, precision=3):

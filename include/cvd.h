@@ -167,7 +167,8 @@ int cvd_conv_fwd(const cvd_src_t* src, const void* packed_w, const float* bias,
 /* The same convolution with the BatchNorm2d(train) batch statistics of its OUTPUT fused into the epilogue
  * (what cvd_bn_stats computes in a separate pass): per-channel sum / sum of squares -> a, b, rstd, mean at
  * physical channels [dst->c_off, +cout) of the arrays, running statistics of this conv's [cout] arrays updated.
- * scratch: cvd_bn_scratch_bytes(256) bytes, zeroed once by the caller (self-cleaning; may be shared with
+ * scratch: cvd_bn_scratch_bytes(cout) bytes (one block per 256 output channels: the 256-column chunks of a wide
+ * conv run concurrently in one launch), zeroed once by the caller (self-cleaning; may be shared with
  * cvd_bn_stats / cvd_bn_bwd_reduce as long as the calls are stream-ordered). */
 typedef struct {
   void* scratch;
@@ -179,6 +180,16 @@ typedef struct {
 int cvd_conv_fwd_bn(const cvd_src_t* src, const void* packed_w, const float* bias,
                     const cvd_dst_t* dst, int N, int H, int W, int cin, int cout, int k,
                     int precision, int flags, const cvd_bn_t* bn, void* stream);
+
+/* nchunks independent convolutions of one shape in ONE launch (blockIdx.y = chunk): chunk j reads the source view
+ * shifted by j * src_shift channels, writes the destination view (bias, BatchNorm arrays) shifted by j * dst_shift
+ * channels and uses the packed weights at packed_w + j * packed_stride bytes.  bn may be NULL; if not, scratch holds
+ * nchunks blocks of cvd_bn_scratch_bytes(256).  Views must be gap-free.  Used for the 64-channel chunks of the grouped
+ * ResNeXt conv2 (midas_v2: blocks.py:23 resnext101_32x8d) -- same results as nchunks cvd_conv_fwd[_bn] calls. */
+int cvd_conv_fwd_chunks(const cvd_src_t* src, const void* packed_w, const float* bias,
+                        const cvd_dst_t* dst, int N, int H, int W, int cin, int cout, int k,
+                        int precision, int flags, const cvd_bn_t* bn,
+                        int nchunks, int src_shift, int dst_shift, long long packed_stride, void* stream);
 
 /* ---- second-generation conv path: pre-split operands + TMA-fed, kx-fused tcgen05 conv (csrc/prep.cu, conv2.cu) ----
  * cvd_prep_operand applies the per-channel transform of `src` (CVD_XF_AFFINE: BatchNorm+ReLU of the producer,
@@ -218,6 +229,13 @@ int cvd_conv2_wgrad(const void* xz, int xc8, int x_off, const void* gz, int gc8,
  * of the chunk's c output / input channels, dw points at the chunk's rows of the (Cout, group_size, k, k) gradient. */
 int cvd_conv_wgrad_grouped(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_ogkk,
                            int N, int H, int W, int c, int group_size, int k, int precision, void* stream);
+
+/* All nchunks chunks of a grouped convolution's weight gradient in ONE launch (blockIdx.z = chunk): gsrc / xsrc are
+ * gap-free views of chunk 0, chunk j reads channels [j*c, (j+1)*c) behind them; dw is the whole (Cout, group_size, k, k)
+ * gradient.  Same result as nchunks cvd_conv_wgrad_grouped calls (ResNeXt conv2 of midas_v2: up to 32 chunks). */
+int cvd_conv_wgrad_grouped_chunks(const cvd_src_t* gsrc, const cvd_src_t* xsrc, float* dw_ogkk,
+                                  int N, int H, int W, int c, int nchunks, int group_size, int k, int precision,
+                                  void* stream);
 
 /* Weight gradient of the same convolution: dW (fp32 OIHW, [cout][cin][k][k]) += sum over all
  * pixels of G (x) X, the wgrad half of autograd's conv backward (depth_fine_tuning.py:282).

@@ -138,6 +138,62 @@ def test_grouped_conv_chunks_forward_dgrad_wgrad(width, H, W):
     assert (dw.double() - wr.grad).abs().max() <= 6e-5 * wr.grad.abs().max()
 
 
+@pytest.mark.parametrize("width,H,W", [(256, 12, 20), (512, 6, 10), (2048, 3, 5)])
+def test_grouped_conv_single_launch_equals_per_chunk_launches(width, H, W):
+    """cvd_conv_fwd_chunks / cvd_conv_wgrad_grouped_chunks (blockIdx = chunk) against the per-chunk launches they
+    replace: forward with BN+ReLU on load and fused output statistics, dgrad, wgrad -- forward / dgrad bit-identical."""
+    from consistent_depth_b200 import ops
+    N, gs, CH = 2, width // 32, 64
+    nch = width // CH
+    xb, gb = nhwc(rnd(20 + width, (N, width, H, W))), nhwc(rnd(21 + width, (N, width, H, W)))
+    w = rnd(22 + width, (width, gs, 3, 3), -0.2, 0.2)
+    a1, b1 = rnd(23, (width,), 0.5, 1.5), rnd(24, (width,), -0.3, 0.3)
+    gamma, beta = rnd(25, (width,), 0.5, 1.5), rnd(26, (width,))
+    nb = ops.packed_bytes(CH, CH, 3, 3)
+    out = {}
+    for mode in ("chunks", "loop"):
+        yb, dxb = torch.zeros(N, H, W, width, device=DEV), torch.zeros(N, H, W, width, device=DEV)
+        dw = torch.zeros_like(w)
+        a, b, rstd, mean = (torch.zeros(width, device=DEV) for _ in range(4))
+        rm, rv = torch.zeros(width, device=DEV), torch.ones(width, device=DEV)
+        pk = torch.cat([ops.pack_weights_grouped(w[j * CH:(j + 1) * CH], CH, gs, False, 3) for j in range(nch)])
+        pkt = torch.cat([ops.pack_weights_grouped(w[j * CH:(j + 1) * CH], CH, gs, True, 3) for j in range(nch)])
+        if mode == "chunks":
+            scratch = ops.bn_scratch(DEV, 256 * nch)
+            bn = ops.make_bn(scratch, a, b, rstd, mean, gamma, beta, rm, rv)
+            ops.conv_chunks(ops.make_src(ops.View(xb, 0), a1, b1, True), pk, None, ops.make_dst(ops.View(yb, 0)), N, H, W,
+                            CH, CH, 3, nch, CH, CH, nb, 3, 0, bn=bn)
+            ops.conv_chunks(ops.make_src(ops.View(gb, 0)), pkt, None, ops.make_dst(ops.View(dxb, 0)), N, H, W,
+                            CH, CH, 3, nch, CH, CH, nb, 3, 0)
+            ops.conv_wgrad_grouped_chunks(ops.make_src(ops.View(gb, 0)), ops.make_src(ops.View(xb, 0), a1, b1, True), dw,
+                                          N, H, W, CH, nch, gs, 3, 3)
+            torch.cuda.synchronize()
+            assert (scratch == 0).all()
+        else:
+            scratch = ops.bn_scratch(DEV)
+            for j in range(nch):
+                c0 = j * CH
+                bn = ops.make_bn(scratch, a, b, rstd, mean, gamma[c0:c0 + CH], beta[c0:c0 + CH], rm[c0:c0 + CH], rv[c0:c0 + CH])
+                ops.conv(ops.make_src(ops.View(xb, c0), a1, b1, True), pk[j * nb:(j + 1) * nb], None, ops.make_dst(ops.View(yb, c0)),
+                         N, H, W, CH, CH, 3, 3, 0, bn=bn)
+                ops.conv(ops.make_src(ops.View(gb, c0)), pkt[j * nb:(j + 1) * nb], None, ops.make_dst(ops.View(dxb, c0)),
+                         N, H, W, CH, CH, 3, 3, 0)
+                ops.conv_wgrad_grouped(ops.make_src(ops.View(gb, c0)), ops.make_src(ops.View(xb, c0), a1, b1, True),
+                                       dw[c0:c0 + CH], N, H, W, CH, gs, 3, 3)
+            torch.cuda.synchronize()
+        out[mode] = (yb, dxb, dw, a, b, rstd, mean, rm, rv)
+    A, B = out["chunks"], out["loop"]
+    assert torch.equal(A[0], B[0]) and torch.equal(A[1], B[1])
+    assert (A[2] - B[2]).abs().max() <= 2e-6 * B[2].abs().max()          # RED order differs (different slab split)
+    for i in range(3, 9):
+        close(A[i], B[i], rtol=1e-5, atol=1e-6)
+    # and against torch
+    xin = torch.relu(nchw(xb).double() * a1.double()[None, :, None, None] + b1.double()[None, :, None, None])
+    ref = F.conv2d(xin, w.double(), None, padding=1, groups=32)
+    assert (nchw(A[0]).double() - ref).abs().max() <= 6e-5 * ref.abs().max()
+    close(A[6].double(), ref.mean((0, 2, 3)), rtol=1e-4, atol=1e-5)
+
+
 # ------------------------------------------------------------------ the network
 def _case():
     c = MIDAS_CASE
@@ -265,7 +321,7 @@ def test_midas_fine_tune_steps_follow_oracle():
         ol.append(float(loss.detach()[0]))
     assert losses[0] == pytest.approx(ol[0], rel=2e-3)
     np.testing.assert_allclose(losses, ol, rtol=5e-2)
-    assert step.launches_per_step > 1000
+    assert 500 < step.launches_per_step < 1200     # grouped / wide convs are single chunked launches (round 1: 2350)
 
 
 def test_midas_registry_and_adapter_surface():

@@ -237,7 +237,7 @@ def test_conv_above_256_channels_forward_dgrad_wgrad(cin, cout, k, H, W):
     a, b, rstd, mean = (torch.zeros(cout, device=DEV) for _ in range(4))
     gamma, beta = rnd(43, (cout,), 0.5, 1.5), rnd(44, (cout,))
     rm, rv = torch.zeros(cout, device=DEV), torch.ones(cout, device=DEV)
-    bn = ops.make_bn(ops.bn_scratch(DEV), a, b, rstd, mean, gamma, beta, rm, rv)
+    bn = ops.make_bn(ops.bn_scratch(DEV, cout), a, b, rstd, mean, gamma, beta, rm, rv)
     ops.conv(ops.make_src(ops.View(xb, 0)), ops.pack_weights(w, False, 3), bias, ops.make_dst(ops.View(yb, 0)), N, H, W, cin, cout, k, 3, 0, bn=bn)
     m = ref.mean((0, 2, 3)); v = ref.var((0, 2, 3), unbiased=False)
     close(mean.double(), m, rtol=1e-4, atol=1e-5)

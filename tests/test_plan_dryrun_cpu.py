@@ -38,7 +38,8 @@ def fake_lib(monkeypatch):
 
 def _wgrad_targets(rec):
     out = collections.Counter()
-    for name, idx in (("cvd_conv_wgrad", 2), ("cvd_conv_wgrad_grouped", 2), ("cvd_conv2_wgrad", 6)):
+    for name, idx in (("cvd_conv_wgrad", 2), ("cvd_conv_wgrad_grouped", 2), ("cvd_conv_wgrad_grouped_chunks", 2),
+                      ("cvd_conv2_wgrad", 6)):
         for a in rec.args[name]:
             out[a[idx].value] += 1
     return out
@@ -50,7 +51,7 @@ def _check_weight_coverage(P, arch, rec, chunk_rows=None):
         if len(shape) != 4 or arch.dead_parameter(k):
             continue
         g = P._g(k)
-        if chunk_rows and shape[1] * 32 == shape[0]:            # grouped (Cout, Cout/32, 3, 3): one launch per 64 output rows
+        if chunk_rows and shape[1] * 32 == shape[0]:            # grouped (Cout, Cout/32, 3, 3): per-chunk launches only
             rows = range(0, shape[0], chunk_rows)
             assert all(targets[g[r:r + 1].data_ptr()] == 1 for r in rows), k
         else:
@@ -93,11 +94,16 @@ def test_midas_plan(fake_lib):
     grouped = [k for k, s in shapes.items() if len(s) == 4 and s[1] * 32 == s[0]]
     chunks = sum(shapes[k][0] // CHUNK for k in grouped)
     assert len(grouped) == 33 and chunks == 508
-    assert fake_lib.calls["cvd_conv_fwd"] + fake_lib.calls["cvd_conv_fwd_bn"] == len(dense) + chunks
+    # every grouped conv is ONE chunked launch (blockIdx.y = 64-channel chunk) forward, one for dgrad, one for wgrad
+    assert fake_lib.calls["cvd_conv_fwd"] + fake_lib.calls["cvd_conv_fwd_bn"] == len(dense)
+    assert fake_lib.calls["cvd_conv_fwd_chunks"] == 33
+    assert sum(a[13] for a in fake_lib.args["cvd_conv_fwd_chunks"]) == chunks
     e.backward(torch.rand(2, 64, 96))
-    assert fake_lib.calls["cvd_conv_wgrad"] == len(dense) and fake_lib.calls["cvd_conv_wgrad_grouped"] == chunks
+    assert fake_lib.calls["cvd_conv_fwd_chunks"] == 66
+    assert fake_lib.calls["cvd_conv_wgrad"] == len(dense) and fake_lib.calls["cvd_conv_wgrad_grouped_chunks"] == 33
+    assert sum(a[7] for a in fake_lib.args["cvd_conv_wgrad_grouped_chunks"]) == chunks
     assert fake_lib.calls["cvd_bn_bwd_reduce"] == 104                                              # 104 BatchNorms
-    _check_weight_coverage(P, midas_arch, fake_lib, chunk_rows=CHUNK)
+    _check_weight_coverage(P, midas_arch, fake_lib)
 
 
 def test_flownet2_op_modules_plumbing(fake_lib):
