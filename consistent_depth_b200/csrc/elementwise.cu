@@ -117,6 +117,16 @@ bn_bwd_reduce_kernel(const float* __restrict__ x, int x_ct, int x_c0,
                      float* __restrict__ dbias)
 {
   extern __shared__ double sh[];                   // [2][C]
+  if (blockIdx.y) {
+    // chunked launch: blockIdx.y = 256-channel chunk of a wider BatchNorm, one statistics block each
+    const int ch = (int)blockIdx.y * 256;
+    x_c0 += ch; dy_lc0 += ch; scratch += (size_t)blockIdx.y * (2 * 256 + 1);
+    if (gamma) gamma += ch;
+    if (beta) beta += ch;
+    if (dgamma) dgamma += ch;
+    if (dbeta) dbeta += ch;
+    if (dbias) dbias += ch;
+  }
   const int cq = C >> 2;
   const int lanes = 256 / cq;
   const int q = threadIdx.x % cq, pl = threadIdx.x / cq;
@@ -425,6 +435,8 @@ extern "C" int cvd_bn_bwd_reduce(const float* x, int x_ctotal, int x_coff,
                                  float* bw, float* dgamma, float* dbeta, float* dbias, void* stream)
 {
   CVD_CHECK_ARG(x && dy && a && b && rstd && mean && scratch && bw, "cvd_bn_bwd_reduce: null pointer");
+  int nchunks = 1;
+  if (C > 256 && C % 256 == 0 && !getenv("CVD_BN_NO_CHUNKS")) { nchunks = C / 256; C = 256; }   // one launch, blockIdx.y = chunk
   if (C > 256) {
     for (int c0 = 0; c0 < C; c0 += 256) {
       const int rc = cvd_bn_bwd_reduce(x, x_ctotal, x_coff + c0, dy, dy_ctotal, dy_coff, dy_n0, dy_gap, dy_lc0 + c0,
@@ -441,10 +453,10 @@ extern "C" int cvd_bn_bwd_reduce(const float* x, int x_ctotal, int x_coff,
   const int lanes = 256 / (C >> 2);
   long long blocks = (npix + lanes * 16 - 1) / ((long long)lanes * 16);
   static const int bpsm = getenv("CVD_BNBWD_BLOCKS") ? atoi(getenv("CVD_BNBWD_BLOCKS")) : 3;
-  const long long cap = (long long)cvd_num_sms() * (bpsm > 0 ? bpsm : 3);
+  const long long cap = ((long long)cvd_num_sms() * (bpsm > 0 ? bpsm : 3) + nchunks - 1) / nchunks;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  bn_bwd_reduce_kernel<<<(unsigned)blocks, 256, 2 * C * sizeof(double), (cudaStream_t)stream>>>(
+  bn_bwd_reduce_kernel<<<dim3((unsigned)blocks, (unsigned)nchunks), 256, 2 * C * sizeof(double), (cudaStream_t)stream>>>(
       x, x_ctotal, x_coff, dy, dy_ctotal, dy_coff, dy_n0 > 0 ? dy_n0 : (1 << 30), dy_gap, dy_lc0, a, b, rstd, mean,
       gamma, beta, relu, npix, C, (double*)scratch, reinterpret_cast<float4*>(bw), dgamma, dbeta, dbias);
   CVD_LAUNCH_OK("bn_bwd_reduce_kernel");
