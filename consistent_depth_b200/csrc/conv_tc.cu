@@ -315,42 +315,52 @@ __device__ __forceinline__ void pack_one(const float* __restrict__ w, int cin_w,
   // logical GEMM dims: K-channels = cin_pad (multiple of 16), N = cout_pad (multiple of 16)
   // GEMM N above 256 (the tcgen05 / TMEM limit of one launch) is packed as independent 256-column chunks, one
   // after the other: chunk j is exactly the blob of a conv with N = min(256, cout_pad - 256 j).
+  // Work item = (column nn, 8 K-channels, tap), nn fastest: a thread writes one 16-B core-matrix row (hi, and lo),
+  // a warp 4 x 128 contiguous bytes; the dgrad (flip) reads are fully coalesced, the forward reads sector-exact.
   const int taps = k * k;
   const int ns2 = nsplit == 3 ? 2 : 1;
-  const long long total = (long long)cin_pad * cout_pad * taps;
+  const int c8n = cin_pad >> 3;
+  const long long total = (long long)cout_pad * c8n * taps;
+  const int flip = transpose_flip & 1, gs = transpose_flip >> 8;   // gs > 0: grouped conv, `gs` channels per group
   for (long long i = first; i < total; i += step) {
-    const int c = (int)(i % cin_pad);
-    const int nn = (int)((i / cin_pad) % cout_pad);
-    const int tap = (int)(i / ((long long)cin_pad * cout_pad));
+    const int nn = (int)(i % cout_pad);
+    const int c0 = (int)((i / cout_pad) % c8n) * 8;
+    const int tap = (int)(i / ((long long)cout_pad * c8n));
     const int ky = tap / k, kx = tap - ky * k;
-    float v = 0.f;
-    const int flip = transpose_flip & 1, gs = transpose_flip >> 8;   // gs > 0: grouped conv, `gs` channels per group
-    if (gs == 0) {
-      if (!flip) {
-        if (c < cin_w && nn < cout_w) v = w[(((size_t)nn * cin_w + c) * k + ky) * k + kx];
-      } else {
-        // GEMM "cin" = forward Cout (w dim 0), GEMM "cout" = forward Cin (w dim 1)
-        if (c < cout_w && nn < cin_w) v = w[(((size_t)c * cin_w + nn) * k + (k - 1 - ky)) * k + (k - 1 - kx)];
+    const int ftap = (k - 1 - ky) * k + (k - 1 - kx);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      float x = 0.f;
+      if (gs == 0) {
+        if (!flip) {
+          if (c < cin_w && nn < cout_w) x = w[((size_t)nn * cin_w + c) * taps + tap];
+        } else {
+          // GEMM "cin" = forward Cout (w dim 0), GEMM "cout" = forward Cin (w dim 1)
+          if (c < cout_w && nn < cin_w) x = w[((size_t)c * cin_w + nn) * taps + ftap];
+        }
+      } else if (c < cin_w && nn < cout_w && c / gs == nn / gs) {
+        // grouped weights (Cout, gs, k, k) expanded block-diagonally into a dense cin_w x cout_w chunk (cin_w == cout_w)
+        if (!flip) x = w[((size_t)nn * gs + c % gs) * taps + tap];
+        else       x = w[((size_t)c * gs + nn % gs) * taps + ftap];
       }
-    } else if (c < cin_w && nn < cout_w && c / gs == nn / gs) {
-      // grouped weights (Cout, gs, k, k) expanded block-diagonally into a dense cin_w x cout_w chunk (cin_w == cout_w)
-      if (!flip) v = w[(((size_t)nn * gs + c % gs) * k + ky) * k + kx];
-      else       v = w[(((size_t)c * gs + nn % gs) * k + (k - 1 - ky)) * k + (k - 1 - kx)];
+      v[j] = x;
     }
     const int nj = nn >> 8, nl = nn & 255;
     const int cp = min(256, cout_pad - (nj << 8));                 // columns of this chunk
     const int stage_bytes = cp * 32 * ns2;
     uint8_t* cout_base = out + (size_t)nj * 256 * cin_pad * taps * 2 * ns2;
-    const int g = c / kGroupCh, cg = c - g * kGroupCh;
+    const int g = c0 / kGroupCh, cg = c0 - g * kGroupCh;
     const int gch = min(kGroupCh, cin_pad - g * kGroupCh);
     const int kbg = gch / 16;
     // stage index: groups before g contribute taps * (their kb count) stages
     const int stage = g * taps * (kGroupCh / 16) + tap * kbg + cg / 16;
-    const int kk = cg & 15;
-    const size_t off = (size_t)stage * stage_bytes + (size_t)(nl >> 3) * 256 + (size_t)(kk >> 3) * 128 + (size_t)(nl & 7) * 16 + (size_t)(kk & 7) * 2;
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    *reinterpret_cast<__nv_bfloat16*>(cout_base + off) = h;
-    if (nsplit == 3) *reinterpret_cast<__nv_bfloat16*>(cout_base + off + (size_t)cp * 32) = __float2bfloat16_rn(v - __bfloat162float(h));
+    const size_t off = (size_t)stage * stage_bytes + (size_t)(nl >> 3) * 256 + (size_t)((cg & 15) >> 3) * 128 + (size_t)(nl & 7) * 16;
+    uint4 hi, lo;
+    tc::split8(v, hi, lo);
+    *reinterpret_cast<uint4*>(cout_base + off) = hi;
+    if (nsplit == 3) *reinterpret_cast<uint4*>(cout_base + off + (size_t)cp * 32) = lo;
   }
 }
 
@@ -392,7 +402,7 @@ extern "C" int cvd_conv_pack_weights(const float* w_oihw, int cin, int cout, int
   const int kc = (transpose_flip & 1) ? cout : cin, nc = (transpose_flip & 1) ? cin : cout;
   const int cin_pad = round_up(kc, 16), cout_pad = round_up(nc, 16);
   const long long total = (long long)cin_pad * cout_pad * k * k;
-  long long blocks = (total + 255) / 256; if (blocks > 4096) blocks = 4096;
+  long long blocks = (total / 8 + 255) / 256; if (blocks > 4096) blocks = 4096; if (blocks < 1) blocks = 1;
   pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, cin, cout, k, transpose_flip,
                                                                           cin_pad, cout_pad, precision, (uint8_t*)packed);
   CVD_LAUNCH_OK("pack_weights_kernel");
@@ -403,7 +413,7 @@ extern "C" int cvd_conv_pack_batch(const void* descs_dev, int n, int precision, 
 {
   CVD_CHECK_ARG(descs_dev && n > 0, "cvd_conv_pack_batch: bad arguments");
   CVD_CHECK_ARG(precision == 1 || precision == 3, "cvd_conv_pack_batch: precision must be 1 or 3");
-  pack_weights_batch_kernel<<<dim3(16, n), 256, 0, (cudaStream_t)stream>>>((const PackDesc*)descs_dev, precision);
+  pack_weights_batch_kernel<<<dim3(32, n), 256, 0, (cudaStream_t)stream>>>((const PackDesc*)descs_dev, precision);
   CVD_LAUNCH_OK("pack_weights_batch_kernel");
   return 0;
 }
