@@ -100,6 +100,9 @@ class Mono2Params:
         return out
 
 
+PAIR_WG = __import__("os").environ.get("CVD_PAIR_WG", "1") != "0"   # run a conv's wgrad and dgrad as parallel graph branches
+
+
 class _BN:
     """One BatchNorm2d (affine): parameters, running statistics and the per-channel arrays the kernels exchange."""
 
@@ -187,7 +190,9 @@ class Mono2Engine:
 
     def _wgrad(self, gsrc, xsrc, wkey, cin, cout, k, h, w):
         dw, N, prec = self._g(wkey), self.N, self.prec
-        self.bwd.append(lambda: ops.conv_wgrad(gsrc, xsrc, dw, N, h, w, cin, cout, k, prec))
+        f = lambda: ops.conv_wgrad(gsrc, xsrc, dw, N, h, w, cin, cout, k, prec)
+        f.wgrad_of = gsrc
+        self.bwd.append(f)
 
     def _dgrad(self, gsrc, wkey, dx, cin, cout, k, h, w, accumulate):
         """dx (tensor, N,h,w,cin) (+)= conv^T(g): a forward conv with GEMM-cin = cout and the flipped/transposed weights."""
@@ -196,7 +201,14 @@ class Mono2Engine:
         self.pack_bwd.append((Wt, pk, True))
         d = ops.make_dst(ops.View(dx, 0))
         N, prec, flags = self.N, self.prec, (ops.FLAG_ACCUM if accumulate else 0)
-        self.bwd.append(lambda: ops.conv(gsrc, pk, None, d, N, h, w, cout, cin, k, prec, flags))
+        f = lambda: ops.conv(gsrc, pk, None, d, N, h, w, cout, cin, k, prec, flags)
+        last = self.bwd[-1] if self.bwd else None
+        if PAIR_WG and getattr(last, "wgrad_of", None) is gsrc:
+            # the weight gradient and the input gradient of one conv read the same gradient view and write different
+            # tensors: two branches of the graph (on the small maps neither fills the GPU alone)
+            self.bwd[-1] = ("par", [[f], [last]])
+        else:
+            self.bwd.append(f)
 
     def _bn_reduce(self, bn, y, dy, relu):
         npix = y.numel() // y.shape[-1]
