@@ -16,3 +16,9 @@ timeout 600 python tools/conv2_microbench.py --wgrad --out gpurun_out/${R}_wgrad
 timeout 300 python tools/profile_engine.py --workload mc --out gpurun_out/${R}_mc_ops_events.json 2>&1 | tail -3
 timeout 400 python bench.py --workload monodepth2 --steps 20 --warmup 5 2>/dev/null | tail -1 > gpurun_out/${R}_bench_monodepth2.json; cut -c1-200 gpurun_out/${R}_bench_monodepth2.json
 timeout 400 python bench.py --workload midas2 --steps 10 --warmup 3 2>/dev/null | tail -1 > gpurun_out/${R}_bench_midas2.json; cut -c1-200 gpurun_out/${R}_bench_midas2.json
+# MiDaS-v2: launch list of one step, the dominant shapes (microbench) and one ncu --set full capture of the wide 1x1 weight gradient
+CVD_PROFILE=1 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${R}_midas_launches_ncu.csv \
+    python bench.py --workload midas2 --steps 1 --warmup 3 --no-cpu-baseline --no-roofline --no-e2e --no-gpu-reference --no-fine-tune-api > gpurun_out/${R}_midas_launches.log 2>&1
+python tools/summarize_launches.py gpurun_out/${R}_midas_launches_ncu.csv --steps 1 > gpurun_out/${R}_midas_launch_summary.json; head -12 gpurun_out/${R}_midas_launch_summary.json
+timeout 300 python tools/midas_microbench.py --out gpurun_out/${R}_midas_microbench.json > gpurun_out/${R}_midas_microbench.txt 2>&1; tail -2 gpurun_out/${R}_midas_microbench.txt | cut -c1-200
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:wgrad_tc_kernel -s 1 -c 1 -o gpurun_out/${R}_ncu_midas_wgrad_1x1 -f python tools/midas_microbench.py --only 1024,1024,1,24,42 --reps 2 > /dev/null 2>&1
