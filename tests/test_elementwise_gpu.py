@@ -22,7 +22,8 @@ def nchw(t):
     return t.permute(0, 3, 1, 2)
 
 
-@pytest.mark.parametrize("C,ct,off,affine", [(32, 32, 0, False), (208, 256, 0, False), (48, 96, 32, False), (128, 128, 0, True)])
+@pytest.mark.parametrize("C,ct,off,affine", [(32, 32, 0, False), (208, 256, 0, False), (48, 96, 32, False), (128, 128, 0, True),
+                                                 (512, 512, 0, True)])      # > 256 channels: one chunked launch (blockIdx.y)
 def test_bn_stats_and_backward_match_torch_batchnorm(C, ct, off, affine):
     from consistent_depth_b200 import ops
     N, H, W = 2, 24, 20
@@ -34,7 +35,7 @@ def test_bn_stats_and_backward_match_torch_batchnorm(C, ct, off, affine):
     xb = torch.zeros(N, H, W, ct, device=DEV); xb[..., off:off + C] = nhwc(x)
     dyb = torch.zeros(N, H, W, ct, device=DEV); dyb[..., off:off + C] = nhwc(dy)
     a = torch.zeros(ct, device=DEV); b = torch.zeros(ct, device=DEV); rstd = torch.zeros(ct, device=DEV); mean = torch.zeros(ct, device=DEV)
-    scratch = ops.bn_scratch(DEV)
+    scratch = ops.bn_scratch(DEV, C)
     npix = N * H * W
     ops.bn_stats(xb, off, C, npix, scratch, a, b, rstd, mean, gamma, beta, rm, rv)
     # torch reference (fp64), train-mode BatchNorm2d + ReLU
