@@ -46,6 +46,30 @@ def test_argument_validation_needs_no_gpu(built_lib):
     assert b"null" in built_lib.cvd_last_error()
 
 
+def test_bn_scratch_holds_one_block_per_256_channels(built_lib):
+    """Chunked launches (blockIdx.y / .z = 256-channel chunk) reduce their chunks concurrently, each into its own
+    [2 x 256 sums | ticket] block of the statistics scratch; the engines size every BatchNorm's scratch for one block per
+    64-channel chunk of a grouped conv (midas_engine.CHUNK)."""
+    built_lib.cvd_bn_scratch_bytes.restype = ctypes.c_size_t
+    block = (2 * 256 + 1) * 8
+    assert built_lib.cvd_bn_scratch_bytes(1) == block and built_lib.cvd_bn_scratch_bytes(256) == block
+    assert built_lib.cvd_bn_scratch_bytes(257) == 2 * block and built_lib.cvd_bn_scratch_bytes(2048) == 8 * block
+    from consistent_depth_b200.monodepth import midas_arch
+    from consistent_depth_b200.monodepth.midas_engine import CHUNK
+    widths = {s[0] for k, s in midas_arch.state_dict_shapes().items() if len(s) == 4 and s[1] * 32 == s[0]}
+    for w in widths:            # _BN allocates cvd_bn_scratch_bytes(max(256, 4 * C)): >= one block per CHUNK channels
+        assert built_lib.cvd_bn_scratch_bytes(max(256, 4 * w)) >= (w // CHUNK) * block
+
+
+def test_chunked_entry_points_validate_arguments_without_gpu(built_lib):
+    built_lib.cvd_last_error.restype = ctypes.c_char_p
+    assert built_lib.cvd_conv_fwd_chunks(None, None, None, None, 1, 8, 8, 64, 64, 3, 3, 0, None, 4, 64, 64,
+                                         ctypes.c_longlong(0), None) != 0
+    assert b"null" in built_lib.cvd_last_error()
+    assert built_lib.cvd_conv_wgrad_grouped_chunks(None, None, None, 1, 8, 8, 64, 4, 8, 3, 3, None) != 0
+    assert b"null" in built_lib.cvd_last_error()
+
+
 def test_product_package_never_imports_oracle():
     pkg = os.path.join(ROOT, "consistent_depth_b200")
     for dp, _, files in os.walk(pkg):
